@@ -1,0 +1,853 @@
+// swrb.cu — host side of libswrb.so: the C ABI declared in include/swrb.h.
+//
+// One swrb_device owns a CUDA stream and the transient work buffers of the pipeline
+//   [cull] -> K1 mesh/setup (+tile count) -> K2 scan -> K2 scatter -> K3 tile raster      (binned)
+//   [cull] -> K1 mesh/setup -> key init -> direct raster (+big) -> key unpack             (unbinned)
+//   -> K5 resolve
+// Every call only enqueues work; nothing here computes pixels on the CPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "cull.cuh"
+#include "mesh.cuh"
+#include "bin.cuh"
+#include "tile.cuh"
+#include "raster_direct.cuh"
+#include "fbops.cuh"
+#include "resolve.cuh"
+
+using namespace swrb;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? SWRB_E_OOM : SWRB_E_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                               \
+    } while (0)
+
+struct StageTimer {
+    cudaEvent_t begin[SWRB_STAGE_COUNT_][8], end[SWRB_STAGE_COUNT_][8];
+    uint32_t used[SWRB_STAGE_COUNT_];
+};
+
+struct swrb_device {
+    int cudaDevice = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    uint32_t flags = SWRB_FLAGS_DEFAULT;
+
+    DevCtl* ctl = nullptr;            // device
+    DevCtl* ctlHost = nullptr;        // pinned mirror
+
+    TriRecord* tris = nullptr;
+    TriRecordW* trisW = nullptr;
+    uint32_t* bigList = nullptr;      // binned: big triangle indices (capacity triCap)
+    BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
+    uint64_t triCap = 0, bigItemCap = 0;
+    uint32_t* binEntries = nullptr;
+    uint64_t binCap = 0;
+    uint64_t reserveTris = 0, reserveBins = 0;
+
+    uint32_t* tileCount = nullptr;    // [numTiles] + offsets [numTiles+1] + cursors [numTiles]
+    uint32_t* tileOffset = nullptr;
+    uint32_t* tileCursor = nullptr;
+    uint32_t tileCap = 0;
+
+    DrawItem* drawItems = nullptr;    // device
+    uint32_t drawItemCap = 0;
+    static constexpr int kStagingSlots = 4;
+    DrawItem* drawStaging[kStagingSlots] = {};
+    uint32_t drawStagingCap[kStagingSlots] = {};
+    cudaEvent_t drawStagingDone[kStagingSlots] = {};
+    int drawStagingNext = 0;
+
+    uint16_t* cullBitmapDev = nullptr;   // result of the last swrb_cull_meshlets
+    uint32_t cullBitmapCap = 0;          // in meshlets
+    uint16_t* cullUpload = nullptr;      // device copy of a host-provided bitmap
+    uint32_t cullUploadCap = 0;
+    uint32_t* visibleDev = nullptr;
+
+    swr_meshlet* hostDrawMeshlets = nullptr;   // scratch scene for swrb_draw_meshlets_host
+    uint32_t hostDrawCap = 0;
+
+    uint32_t* detileScratch = nullptr;
+    size_t detileCap = 0;
+
+    void* l2Scratch = nullptr;
+    size_t l2ScratchBytes = 0;
+
+    cudaEvent_t timerBegin = nullptr, timerEnd = nullptr;
+    bool stageTiming = false;
+    StageTimer* st = nullptr;
+    uint64_t launches = 0;
+    uint64_t hostTimeNs[SWR_PERF_Count_] = {};
+};
+
+struct DeviceTexture {     // Texture2D<RGBA8u, TiledY8> (Texture.h:314-329)
+    swr_texture_desc desc;
+    uint32_t* data;
+};
+
+struct swrb_scene {
+    swrb_device* dev;
+    swr_meshlet* meshlets = nullptr;
+    uint32_t numMeshlets = 0;
+    swr_material* materials = nullptr;
+    uint32_t numMaterials = 0;
+    ResolveTexture* textures = nullptr;   // device table
+    std::vector<uint32_t*> textureData;
+    uint32_t numTextures = 0;
+    swr_light* lights = nullptr;
+    uint32_t numLights = 0;
+    bool hasAlphaTest = false;
+};
+
+struct swrb_fb {
+    swrb_device* dev;
+    uint32_t width, height, layers, layerStride;
+    uint32_t* data = nullptr;
+    unsigned long long* keys = nullptr;   // direct path only (lazily allocated)
+    bool pendingClear = false;            // Clear() recorded but not yet materialised (fused into the next draw)
+    uint32_t clearColor = 0, clearDepthBits = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct StageScope {
+    swrb_device* d; int stage; int slot = -1;
+    StageScope(swrb_device* dev, int s) : d(dev), stage(s) {
+        if (d->stageTiming && d->st->used[s] < 8) {
+            slot = (int)d->st->used[s]++;
+            cudaEventRecord(d->st->begin[s][slot], d->stream);
+        }
+    }
+    ~StageScope() {
+        if (slot >= 0) cudaEventRecord(d->st->end[stage][slot], d->stream);
+    }
+};
+
+static inline uint32_t grid_for(const swrb_device* d, uint64_t items, uint32_t perBlock, uint32_t blocksPerSM) {
+    uint64_t need = (items + perBlock - 1) / perBlock;
+    uint64_t cap = (uint64_t)d->numSMs * blocksPerSM;
+    return (uint32_t)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+static int ensure_buffer(void** ptr, uint64_t* cap, uint64_t need, size_t elem) {
+    if (need <= *cap && *ptr != nullptr) return SWRB_OK;
+    if (*ptr) CU(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    CU(cudaMalloc(ptr, need * elem));
+    *cap = need;
+    return SWRB_OK;
+}
+
+static int check_overflow(swrb_device* d) {
+    // caller has synchronised the stream
+    CU(cudaMemcpy(d->ctlHost, d->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost));
+    if (d->ctlHost->overflow) {
+        uint32_t which = d->ctlHost->overflow;
+        uint32_t zero = 0;
+        cudaMemcpy(&d->ctl->overflow, &zero, 4, cudaMemcpyHostToDevice);
+        return fail(SWRB_E_BIN_OVERFLOW,
+                    "device work list overflowed (%s); the draw was aborted before touching the framebuffer — "
+                    "call swrb_device_reserve() with larger limits and redraw",
+                    which == 1 ? "triangle records" : which == 2 ? "big-triangle work items" : "tile bin entries");
+    }
+    return SWRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* swrb_last_error(void) { return g_lastError.c_str(); }
+const char* swrb_version(void) { return "swrb 0.1 (sm_100a)"; }
+
+int swrb_device_create(int cuda_device, swrb_device** out) {
+    if (!out) return fail(SWRB_E_INVALID, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SWRB_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cuda_device < 0 || cuda_device >= n) return fail(SWRB_E_INVALID, "cuda_device %d out of range (%d devices)", cuda_device, n);
+    CU(cudaSetDevice(cuda_device));
+    swrb_device* d = new swrb_device();
+    d->cudaDevice = cuda_device;
+    CU(cudaDeviceGetAttribute(&d->numSMs, cudaDevAttrMultiProcessorCount, cuda_device));
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&d->ctl, sizeof(DevCtl)));
+    CU(cudaMemset(d->ctl, 0, sizeof(DevCtl)));
+    CU(cudaMallocHost(&d->ctlHost, sizeof(DevCtl)));
+    CU(cudaMalloc(&d->visibleDev, 4));
+    CU(cudaEventCreate(&d->timerBegin));
+    CU(cudaEventCreate(&d->timerEnd));
+    for (int i = 0; i < swrb_device::kStagingSlots; i++) CU(cudaEventCreateWithFlags(&d->drawStagingDone[i], cudaEventDisableTiming));
+    *out = d;
+    return SWRB_OK;
+}
+
+void swrb_device_destroy(swrb_device* d) {
+    if (!d) return;
+    cudaSetDevice(d->cudaDevice);
+    cudaStreamSynchronize(d->stream);
+    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->bigList);
+    cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
+    for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
+    cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
+    cudaFree(d->detileScratch); cudaFree(d->l2Scratch);
+    cudaEventDestroy(d->timerBegin); cudaEventDestroy(d->timerEnd);
+    if (d->st) {
+        for (int s = 0; s < SWRB_STAGE_COUNT_; s++)
+            for (int k = 0; k < 8; k++) { cudaEventDestroy(d->st->begin[s][k]); cudaEventDestroy(d->st->end[s][k]); }
+        delete d->st;
+    }
+    if (d->ownStream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int swrb_device_set_stream(swrb_device* d, void* cuda_stream) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->ownStream) { CU(cudaStreamDestroy(d->stream)); }
+    if (cuda_stream) { d->stream = (cudaStream_t)cuda_stream; d->ownStream = false; }
+    else { CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)); d->ownStream = true; }
+    return SWRB_OK;
+}
+
+int swrb_device_set_flags(swrb_device* d, uint32_t flags) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    d->flags = flags;
+    return SWRB_OK;
+}
+
+int swrb_device_reserve(swrb_device* d, uint64_t max_triangles, uint64_t max_bin_entries) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    d->reserveTris = max_triangles;
+    d->reserveBins = max_bin_entries;
+    return SWRB_OK;
+}
+
+int swrb_sync(swrb_device* d) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));
+    return check_overflow(d);
+}
+
+int swrb_get_counters(swrb_device* d, uint64_t out[SWR_PERF_Count_]) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));
+    int rc = check_overflow(d);
+    if (rc) return rc;
+    for (int i = 0; i < 4; i++) out[i] = d->ctlHost->perf[i];
+    for (int i = 4; i < SWR_PERF_Count_; i++) out[i] = d->hostTimeNs[i];
+    return SWRB_OK;
+}
+
+int swrb_reset_counters(swrb_device* d) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaMemsetAsync(d->ctl->perf, 0, sizeof(d->ctl->perf), d->stream));
+    memset(d->hostTimeNs, 0, sizeof(d->hostTimeNs));
+    return SWRB_OK;
+}
+
+// ---- scene -------------------------------------------------------------------------------------
+int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_meshlets, const swr_material* materials,
+                      uint32_t num_materials, const swr_texture_desc* textures, uint32_t num_textures,
+                      const swr_light* lights, uint32_t num_lights, swrb_scene** out) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    if (num_meshlets && !meshlets) return fail(SWRB_E_INVALID, "meshlets is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    swrb_scene* s = new swrb_scene();
+    s->dev = d;
+    s->numMeshlets = num_meshlets;
+    if (num_meshlets) {
+        CU(cudaMalloc(&s->meshlets, (size_t)num_meshlets * sizeof(swr_meshlet)));
+        CU(cudaMemcpyAsync(s->meshlets, meshlets, (size_t)num_meshlets * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
+    }
+    s->numMaterials = num_materials;
+    if (num_materials) {
+        for (uint32_t i = 0; i < num_materials; i++) {
+            if (materials[i].AlphaCutoff < 255) s->hasAlphaTest = true;
+            if (materials[i].TextureId >= (int32_t)num_textures) return fail(SWRB_E_INVALID, "material %u references texture %d of %u", i, materials[i].TextureId, num_textures);
+        }
+        CU(cudaMalloc(&s->materials, num_materials * sizeof(swr_material)));
+        CU(cudaMemcpyAsync(s->materials, materials, num_materials * sizeof(swr_material), cudaMemcpyHostToDevice, d->stream));
+    }
+    s->numTextures = num_textures;
+    if (num_textures) {
+        std::vector<ResolveTexture> table(num_textures);
+        for (uint32_t i = 0; i < num_textures; i++) {
+            const swr_texture_desc& t = textures[i];
+            size_t texels = (size_t)t.LayerStride * t.NumLayers;
+            uint32_t* dev = nullptr;
+            CU(cudaMalloc(&dev, texels * 4 + 256));
+            CU(cudaMemcpyAsync(dev, t.Data, texels * 4, cudaMemcpyHostToDevice, d->stream));
+            s->textureData.push_back(dev);
+            ResolveTexture& r = table[i];
+            r.data = dev;
+            r.width = t.Width; r.height = t.Height; r.mipLevels = t.MipLevels; r.numLayers = t.NumLayers;
+            r.rowShift = t.RowShift; r.layerStride = t.LayerStride;
+            for (int m = 0; m < 16; m++) r.mipOffsets[m] = t.MipOffsets[m];
+        }
+        CU(cudaMalloc(&s->textures, num_textures * sizeof(ResolveTexture)));
+        CU(cudaMemcpy(s->textures, table.data(), num_textures * sizeof(ResolveTexture), cudaMemcpyHostToDevice));
+    }
+    s->numLights = num_lights;
+    if (num_lights) {
+        CU(cudaMalloc(&s->lights, num_lights * sizeof(swr_light)));
+        CU(cudaMemcpyAsync(s->lights, lights, num_lights * sizeof(swr_light), cudaMemcpyHostToDevice, d->stream));
+    }
+    CU(cudaStreamSynchronize(d->stream));   // host inputs are only borrowed for the duration of the call
+    *out = s;
+    return SWRB_OK;
+}
+
+int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint32_t first, uint32_t count) {
+    if (!s || !meshlets) return fail(SWRB_E_INVALID, "null argument");
+    if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
+    CU(cudaSetDevice(s->dev->cudaDevice));
+    CU(cudaMemcpyAsync(s->meshlets + first, meshlets, (size_t)count * sizeof(swr_meshlet), cudaMemcpyHostToDevice, s->dev->stream));
+    return SWRB_OK;
+}
+
+void swrb_scene_destroy(swrb_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->dev->cudaDevice);
+    cudaStreamSynchronize(s->dev->stream);
+    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights);
+    for (uint32_t* p : s->textureData) cudaFree(p);
+    delete s;
+}
+
+// ---- framebuffer -------------------------------------------------------------------------------
+int swrb_fb_create(swrb_device* d, uint32_t width, uint32_t height, uint32_t num_layers, swrb_fb** out) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    if (width == 0 || height == 0 || width % 4 || height % 4) return fail(SWRB_E_INVALID, "framebuffer size %ux%u must be a non-zero multiple of 4 (Rasterizer.h:67)", width, height);
+    if (width > SWR_MAX_RENDER_SIZE || height > SWR_MAX_RENDER_SIZE) return fail(SWRB_E_INVALID, "framebuffer size %ux%u exceeds MaxRenderSize %d (Rasterizer.h:203)", width, height, SWR_MAX_RENDER_SIZE);
+    if (num_layers < 2) return fail(SWRB_E_INVALID, "need at least 2 layers (colour/id + depth)");
+    CU(cudaSetDevice(d->cudaDevice));
+    swrb_fb* fb = new swrb_fb();
+    fb->dev = d; fb->width = width; fb->height = height; fb->layers = num_layers;
+    fb->layerStride = (width * height + 63u) & ~63u;                      // Rasterizer.h:69
+    CU(cudaMalloc(&fb->data, (size_t)fb->layerStride * num_layers * 4 + 256));
+    CU(cudaMemsetAsync(fb->data, 0, (size_t)fb->layerStride * num_layers * 4, d->stream));
+    *out = fb;
+    return SWRB_OK;
+}
+
+void swrb_fb_destroy(swrb_fb* fb) {
+    if (!fb) return;
+    cudaSetDevice(fb->dev->cudaDevice);
+    cudaStreamSynchronize(fb->dev->stream);
+    cudaFree(fb->data); cudaFree(fb->keys);
+    delete fb;
+}
+
+int swrb_fb_info(const swrb_fb* fb, swr_fb_info* out) {
+    if (!fb || !out) return fail(SWRB_E_INVALID, "null argument");
+    out->Width = fb->width; out->Height = fb->height; out->TileStride = fb->width / 4;
+    out->LayerStride = fb->layerStride; out->NumLayers = fb->layers;
+    return SWRB_OK;
+}
+
+static int fb_clear_layer_now(swrb_fb* fb, uint32_t layerA, uint32_t valueA, int layerB, uint32_t valueB) {
+    swrb_device* d = fb->dev;
+    uint32_t numVec = fb->width * fb->height / 4;
+    StageScope ss(d, SWRB_STAGE_CLEAR);
+    k_fb_clear<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
+        reinterpret_cast<uint4*>(fb->data + (size_t)layerA * fb->layerStride), valueA,
+        layerB >= 0 ? reinterpret_cast<uint4*>(fb->data + (size_t)layerB * fb->layerStride) : nullptr, valueB, numVec);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+static int fb_materialize_clear(swrb_fb* fb) {
+    if (!fb->pendingClear) return SWRB_OK;
+    fb->pendingClear = false;
+    return fb_clear_layer_now(fb, 0, fb->clearColor, 1, fb->clearDepthBits);
+}
+
+int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    if (!(depth >= 0.0f)) return fail(SWRB_E_INVALID, "clear depth must be >= 0 (reverse-Z, Main.cpp:213)");
+    // Recorded, not executed: the next draw performs the clear while it writes the tiles
+    // (or any other access materialises it first).
+    uint32_t bits; memcpy(&bits, &depth, 4);
+    if (bits == 0x80000000u) bits = 0;
+    fb->pendingClear = true;
+    fb->clearColor = color;
+    fb->clearDepthBits = bits;
+    return SWRB_OK;
+}
+
+int swrb_fb_clear_layer(swrb_fb* fb, uint32_t layer, uint32_t value) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
+    CU(cudaSetDevice(fb->dev->cudaDevice));
+    int rc = fb_materialize_clear(fb);
+    if (rc) return rc;
+    return fb_clear_layer_now(fb, layer, value, -1, 0);
+}
+
+int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host) {
+    if (!fb || !dst_host) return fail(SWRB_E_INVALID, "null argument");
+    if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
+    CU(cudaSetDevice(fb->dev->cudaDevice));
+    int rc = fb_materialize_clear(fb);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst_host, fb->data + (size_t)layer * fb->layerStride, (size_t)fb->width * fb->height * 4, cudaMemcpyDeviceToHost, fb->dev->stream));
+    CU(cudaStreamSynchronize(fb->dev->stream));
+    return check_overflow(fb->dev);
+}
+
+int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host) {
+    if (!fb || !src_host) return fail(SWRB_E_INVALID, "null argument");
+    if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
+    CU(cudaSetDevice(fb->dev->cudaDevice));
+    int rc = fb_materialize_clear(fb);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(fb->data + (size_t)layer * fb->layerStride, src_host, (size_t)fb->width * fb->height * 4, cudaMemcpyHostToDevice, fb->dev->stream));
+    CU(cudaStreamSynchronize(fb->dev->stream));
+    return SWRB_OK;
+}
+
+int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride) {
+    if (!fb || !dst_device) return fail(SWRB_E_INVALID, "null argument");
+    if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
+    if (stride < fb->width || stride % 4) return fail(SWRB_E_INVALID, "stride %u must be >= width and a multiple of 4", stride);
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    int rc = fb_materialize_clear(fb);
+    if (rc) return rc;
+    uint32_t numVec = fb->width * fb->height / 4;
+    k_fb_detile<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
+        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {
+    if (!fb || !dst_host) return fail(SWRB_E_INVALID, "null argument");
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    size_t need = (size_t)fb->width * fb->height;
+    if (d->detileCap < need) {
+        if (d->detileScratch) CU(cudaFree(d->detileScratch));
+        d->detileScratch = nullptr; d->detileCap = 0;
+        CU(cudaMalloc(&d->detileScratch, need * 4));
+        d->detileCap = need;
+    }
+    int rc = swrb_fb_get_pixels_device(fb, layer, d->detileScratch, fb->width);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch, (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaStreamSynchronize(d->stream));
+    return check_overflow(d);
+}
+
+// ---- culling -----------------------------------------------------------------------------------
+// glm::mat4 * glm::mat4 on column-major arrays: column c of the result is the combination of a's
+// columns weighted by b's column c, summed left to right.
+static void mat4_mul(const float* a, const float* b, float* r) {
+    float t[16];
+    for (int c = 0; c < 4; c++)
+        for (int k = 0; k < 4; k++) {
+            float acc = a[0 * 4 + k] * b[c * 4 + 0];
+            acc = acc + a[1 * 4 + k] * b[c * 4 + 1];
+            acc = acc + a[2 * 4 + k] * b[c * 4 + 2];
+            acc = acc + a[3 * 4 + k] * b[c * 4 + 3];
+            t[c * 4 + k] = acc;
+        }
+    memcpy(r, t, sizeof(t));
+}
+
+int swrb_frustum_planes(const float proj[16], const float view[16], const float model[16], float planes_out[5][4]) {
+    if (!proj || !view || !model || !planes_out) return fail(SWRB_E_INVALID, "null argument");
+    float pv[16], m[16];
+    mat4_mul(proj, view, pv);
+    mat4_mul(pv, model, m);                                       // Shading.cpp:781
+    float planes[6][4];
+    for (int i = 0; i < 3; i++) {                                 // Shading.cpp:784-791 (rows of the transposed matrix)
+        float pa[4], pb[4];
+        for (int c = 0; c < 4; c++) { pa[c] = m[c * 4 + 3] + m[c * 4 + i]; pb[c] = m[c * 4 + 3] - m[c * 4 + i]; }
+        float la = sqrtf((pa[0] * pa[0] + pa[1] * pa[1]) + pa[2] * pa[2]);
+        float lb = sqrtf((pb[0] * pb[0] + pb[1] * pb[1]) + pb[2] * pb[2]);
+        for (int c = 0; c < 4; c++) { planes[i * 2][c] = pa[c] / la; planes[i * 2 + 1][c] = pb[c] / lb; }
+    }
+    memcpy(planes_out, planes, 5 * 4 * sizeof(float));            // plane 5 is never tested (Shading.cpp:806)
+    return SWRB_OK;
+}
+
+int swrb_cull_meshlets(swrb_scene* s, uint32_t meshlet_offset, uint32_t count, const float proj[16], const float view[16],
+                       const float model[16], uint16_t* bitmap_out_host, uint32_t* visible_out) {
+    if (!s) return fail(SWRB_E_INVALID, "scene is null");
+    if ((uint64_t)meshlet_offset + count > s->numMeshlets) return fail(SWRB_E_INVALID, "meshlet range out of bounds");
+    swrb_device* d = s->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    CullPlanes planes;
+    int rc = swrb_frustum_planes(proj, view, model, planes.p);
+    if (rc) return rc;
+    uint32_t words32 = (count + 31) / 32;
+    if (d->cullBitmapCap < words32 * 32 || !d->cullBitmapDev) {
+        if (d->cullBitmapDev) CU(cudaFree(d->cullBitmapDev));
+        d->cullBitmapDev = nullptr;
+        CU(cudaMalloc(&d->cullBitmapDev, (size_t)std::max(words32, 1u) * 4));
+        d->cullBitmapCap = words32 * 32;
+    }
+    CU(cudaMemsetAsync(d->visibleDev, 0, 4, d->stream));
+    if (count) {
+        StageScope ss(d, SWRB_STAGE_CULL);
+        k_cull_meshlets<<<(count + 255) / 256, 256, 0, d->stream>>>(s->meshlets + meshlet_offset, count, planes,
+                                                                    reinterpret_cast<uint32_t*>(d->cullBitmapDev), d->visibleDev);
+        d->launches++;
+        CU(cudaGetLastError());
+    }
+    if (bitmap_out_host || visible_out) {
+        if (bitmap_out_host && count) {
+            // the kernel writes whole u32 words; copy only the u16 words the caller's array has
+            CU(cudaMemcpyAsync(bitmap_out_host, d->cullBitmapDev, (size_t)((count + 15) / 16) * 2, cudaMemcpyDeviceToHost, d->stream));
+        }
+        uint32_t vis = 0;
+        CU(cudaMemcpyAsync(&vis, d->visibleDev, 4, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        if (visible_out) *visible_out = vis;
+    }
+    return SWRB_OK;
+}
+
+// ---- draw --------------------------------------------------------------------------------------
+static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bool alphaTest) {
+    uint64_t needTris = std::max<uint64_t>(std::max<uint64_t>(maxTris, d->reserveTris), 1024);
+    if (needTris > d->triCap) {
+        needTris = needTris + needTris / 4;
+        uint64_t cap = d->triCap;
+        int rc = ensure_buffer((void**)&d->tris, &cap, needTris, sizeof(TriRecord));
+        if (rc) return rc;
+        if (d->bigList) { CU(cudaFree(d->bigList)); d->bigList = nullptr; }
+        CU(cudaMalloc(&d->bigList, needTris * 4));
+        if (d->trisW) { CU(cudaFree(d->trisW)); d->trisW = nullptr; }
+        d->triCap = needTris;
+    }
+    if (alphaTest && !d->trisW) CU(cudaMalloc(&d->trisW, d->triCap * sizeof(TriRecordW)));
+    uint64_t needBins = std::max<uint64_t>(d->reserveBins, 2 * d->triCap + (1u << 20));
+    if (needBins > d->binCap) {
+        int rc = ensure_buffer((void**)&d->binEntries, &d->binCap, needBins, 4);
+        if (rc) return rc;
+    }
+    uint64_t needBig = std::max<uint64_t>(1u << 20, d->triCap / 2);
+    if (needBig > d->bigItemCap) {
+        int rc = ensure_buffer((void**)&d->bigItems, &d->bigItemCap, needBig, sizeof(BigItem));
+        if (rc) return rc;
+    }
+    uint32_t tilesX = (fb->width + kTileSize - 1) >> kTileShift, tilesY = (fb->height + kTileSize - 1) >> kTileShift;
+    uint32_t numTiles = tilesX * tilesY;
+    if (numTiles > d->tileCap) {
+        if (d->tileCount) CU(cudaFree(d->tileCount));
+        d->tileCount = nullptr;
+        CU(cudaMalloc(&d->tileCount, ((size_t)numTiles * 3 + 4) * 4));
+        d->tileOffset = d->tileCount + numTiles;
+        d->tileCursor = d->tileOffset + numTiles + 1;
+        d->tileCap = numTiles;
+    } else {
+        d->tileOffset = d->tileCount + d->tileCap;
+        d->tileCursor = d->tileOffset + d->tileCap + 1;
+    }
+    return SWRB_OK;
+}
+
+static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool binned) {
+    FrameParams fp;
+    fp.width = fb->width; fp.height = fb->height;
+    fp.halfW = (int32_t)fb->width / 2; fp.halfH = (int32_t)fb->height / 2;          // Rasterizer.cpp:508
+    fp.fixX = (float)(fp.halfW * 16); fp.fixY = (float)(fp.halfH * 16);               // :272
+    bool guard = binned || (d->flags & SWRB_FLAG_GUARDBAND);                          // :509 vs :155-156
+    fp.bx = guard ? (float)SWR_MAX_RENDER_SIZE / (float)fb->width : 1.0f;
+    fp.by = guard ? (float)SWR_MAX_RENDER_SIZE / (float)fb->height : 1.0f;
+    fp.tilesX = (fb->width + kTileSize - 1) >> kTileShift;
+    fp.tilesY = (fb->height + kTileSize - 1) >> kTileShift;
+    fp.layerStride = fb->layerStride;
+    return fp;
+}
+
+static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
+                         bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws) {
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    if (numDraws == 0) return SWRB_OK;
+    const bool binned = (d->flags & SWRB_FLAG_BINNING) != 0;
+
+    // ---- per-draw items
+    uint64_t totalWork = 0;
+    for (uint32_t i = 0; i < numDraws; i++) {
+        if ((uint64_t)draws[i].MeshletOffset + draws[i].MeshletCount > numMeshletsDev)
+            return fail(SWRB_E_INVALID, "draw %u: meshlet range [%u,+%u) exceeds the scene's %u meshlets", i, draws[i].MeshletOffset, draws[i].MeshletCount, numMeshletsDev);
+        totalWork += draws[i].MeshletCount;
+    }
+    if (totalWork == 0) return SWRB_OK;
+    if (totalWork >= (1ull << 25)) return fail(SWRB_E_INVALID, "too many meshlets in one batch");
+    int rc = ensure_work_buffers(d, fb, totalWork * SWR_MAX_PRIMS, alphaTest);
+    if (rc) return rc;
+
+    if (numDraws > d->drawItemCap) {
+        if (d->drawItems) CU(cudaFree(d->drawItems));
+        d->drawItems = nullptr;
+        CU(cudaMalloc(&d->drawItems, (size_t)numDraws * sizeof(DrawItem)));
+        d->drawItemCap = numDraws;
+    }
+    int slot = d->drawStagingNext;
+    d->drawStagingNext = (slot + 1) % swrb_device::kStagingSlots;
+    if (d->drawStagingCap[slot] < numDraws) {
+        CU(cudaEventSynchronize(d->drawStagingDone[slot]));
+        if (d->drawStaging[slot]) CU(cudaFreeHost(d->drawStaging[slot]));
+        d->drawStaging[slot] = nullptr;
+        CU(cudaMallocHost(&d->drawStaging[slot], (size_t)numDraws * sizeof(DrawItem)));
+        d->drawStagingCap[slot] = numDraws;
+    } else {
+        CU(cudaEventSynchronize(d->drawStagingDone[slot]));
+    }
+    DrawItem* items = d->drawStaging[slot];
+    uint32_t firstWork = 0;
+    size_t cullWords = 0;
+    for (uint32_t i = 0; i < numDraws; i++) if (draws[i].CullBitmapHost) cullWords += (draws[i].MeshletCount + 15) / 16 + 1;
+    if (cullWords > d->cullUploadCap) {
+        if (d->cullUpload) CU(cudaFree(d->cullUpload));
+        d->cullUpload = nullptr;
+        CU(cudaMalloc(&d->cullUpload, cullWords * 2));
+        d->cullUploadCap = (uint32_t)cullWords;
+    }
+    size_t cullCursor = 0;
+    for (uint32_t i = 0; i < numDraws; i++) {
+        DrawItem& it = items[i];
+        memcpy(it.M, draws[i].ObjectToClip, sizeof(it.M));
+        memcpy(it.planes, draws[i].FrustumPlanes, sizeof(it.planes));
+        it.meshletOffset = draws[i].MeshletOffset;
+        it.count = draws[i].MeshletCount;
+        it.firstWork = firstWork;
+        it.fusedCull = (d->flags & SWRB_FLAG_FUSED_FRUSTUM_CULL) ? 1u : 0u;
+        it.cullBitmap = nullptr;
+        if (draws[i].CullBitmapHost) {
+            size_t words = (draws[i].MeshletCount + 15) / 16;
+            CU(cudaMemcpyAsync(d->cullUpload + cullCursor, draws[i].CullBitmapHost, words * 2, cudaMemcpyHostToDevice, d->stream));
+            it.cullBitmap = d->cullUpload + cullCursor;
+            cullCursor += words + (words & 1);
+        } else if (draws[i].UseDeviceCullBitmap) {
+            if (!d->cullBitmapDev || d->cullBitmapCap < draws[i].MeshletCount)
+                return fail(SWRB_E_INVALID, "draw %u: UseDeviceCullBitmap without a preceding swrb_cull_meshlets of >= %u meshlets", i, draws[i].MeshletCount);
+            it.cullBitmap = d->cullBitmapDev;
+        }
+        firstWork += draws[i].MeshletCount;
+    }
+    CU(cudaMemcpyAsync(d->drawItems, items, (size_t)numDraws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
+    CU(cudaEventRecord(d->drawStagingDone[slot], d->stream));
+
+    FrameParams fp = frame_params(d, fb, binned);
+    const uint32_t numTiles = fp.tilesX * fp.tilesY;
+    const uint32_t numVec = fb->width * fb->height / 4;
+    uint32_t* colorLayer = fb->data;
+    uint32_t* depthLayer = fb->data + fb->layerStride;
+
+    // transient counters (triCount, bigCount, binTotal keep `overflow` sticky until the host reads it)
+    CU(cudaMemsetAsync(d->ctl, 0, offsetof(DevCtl, overflow), d->stream));
+
+    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 8);
+    if (binned) {
+        CU(cudaMemsetAsync(d->tileCount, 0, (size_t)numTiles * 4, d->stream));
+        {
+            StageScope ss(d, SWRB_STAGE_MESH);
+            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp,
+                                                                           d->tris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, d->ctl);
+            d->launches++;
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_BIN);
+            k_tile_scan<<<1, 1024, 0, d->stream>>>(d->tileCount, d->tileOffset, d->tileCursor, numTiles, (uint32_t)std::min<uint64_t>(d->binCap, 0xFFFFFFFFu), d->ctl);
+            k_bin_scatter<<<grid_for(d, d->triCap, 256, 8), 256, 0, d->stream>>>(d->tris, fp, d->tileOffset, d->tileCursor, d->binEntries, d->ctl);
+            d->launches += 2;
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_RASTER);
+            int clearMode = fb->pendingClear ? 1 : 0;
+            k_tile_raster<<<numTiles, kTileThreads, 0, d->stream>>>(d->tris, d->tileOffset, d->binEntries, d->bigList, fp, colorLayer, depthLayer,
+                                                                    clearMode, fb->clearColor, fb->clearDepthBits, d->ctl);
+            d->launches++;
+            // on overflow the tile kernel returns without touching the framebuffer, so the recorded
+            // clear has to survive; otherwise it has just been performed.
+            // (overflow is detected at the next synchronising call, which reports an error.)
+            fb->pendingClear = false;
+        }
+    } else {
+        if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
+        {
+            StageScope ss(d, SWRB_STAGE_MESH);
+            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp,
+                                                                            d->tris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr, d->ctl);
+            d->launches++;
+        }
+        rc = fb_materialize_clear(fb);
+        if (rc) return rc;
+        {
+            StageScope ss(d, SWRB_STAGE_RASTER);
+            k_keys_init<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const uint4*>(depthLayer), reinterpret_cast<ulonglong2*>(fb->keys), numVec);
+            k_raster_direct<<<grid_for(d, d->triCap, 256, 8), 256, 0, d->stream>>>(d->tris, fp, fb->keys, d->bigItems, (uint32_t)std::min<uint64_t>(d->bigItemCap, 0xFFFFFFFFu), d->ctl);
+            k_raster_big<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
+            k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const ulonglong2*>(fb->keys), reinterpret_cast<uint4*>(colorLayer), reinterpret_cast<uint4*>(depthLayer), numVec);
+            d->launches += 4;
+        }
+    }
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws) {
+    if (!fb || !scene || (!draws && num_draws)) return fail(SWRB_E_INVALID, "null argument");
+    if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
+    return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->hasAlphaTest, draws, num_draws);
+}
+
+int swrb_draw_meshlets(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draw) {
+    return swrb_draw_batch(fb, scene, draw, 1);
+}
+
+int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint32_t count, const float object_to_clip[16],
+                            const uint16_t* cull_bitmap_host) {
+    if (!fb || !meshlets_host || !object_to_clip) return fail(SWRB_E_INVALID, "null argument");
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    if (count > d->hostDrawCap) {
+        if (d->hostDrawMeshlets) CU(cudaFree(d->hostDrawMeshlets));
+        d->hostDrawMeshlets = nullptr; d->hostDrawCap = 0;
+        CU(cudaMalloc(&d->hostDrawMeshlets, (size_t)count * sizeof(swr_meshlet)));
+        d->hostDrawCap = count;
+    }
+    CU(cudaMemcpyAsync(d->hostDrawMeshlets, meshlets_host, (size_t)count * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
+    swrb_draw_desc desc;
+    memset(&desc, 0, sizeof(desc));
+    desc.MeshletOffset = 0;
+    desc.MeshletCount = count;
+    memcpy(desc.ObjectToClip, object_to_clip, sizeof(desc.ObjectToClip));
+    desc.CullBitmapHost = cull_bitmap_host;
+    return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, false, &desc, 1);
+}
+
+// ---- resolve -----------------------------------------------------------------------------------
+int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u) {
+    if (!fb || !scene || !u) return fail(SWRB_E_INVALID, "null argument");
+    if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    int rc = fb_materialize_clear(fb);
+    if (rc) return rc;
+    ResolveParams rp;
+    memcpy(rp.objectToClip, u->ObjectToClip, sizeof(rp.objectToClip));
+    memcpy(rp.objectToWorld, u->ObjectToWorld, sizeof(rp.objectToWorld));
+    memcpy(rp.invScreenProj, u->InvScreenProj, sizeof(rp.invScreenProj));
+    memcpy(rp.viewPos, u->ViewPos, sizeof(rp.viewPos));
+    rp.exposure = u->Exposure;
+    rp.width = fb->width; rp.height = fb->height;
+    rp.meshlets = scene->meshlets; rp.materials = scene->materials; rp.textures = scene->textures;
+    rp.lights = scene->lights; rp.numLights = scene->numLights; rp.numMeshlets = scene->numMeshlets;
+    rp.color = fb->data; rp.depth = fb->data + fb->layerStride;
+    {
+        StageScope ss(d, SWRB_STAGE_RESOLVE);
+        dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
+        k_resolve<<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        d->launches++;
+    }
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+// ---- timing ------------------------------------------------------------------------------------
+int swrb_timer_begin(swrb_device* d) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaEventRecord(d->timerBegin, d->stream));
+    return SWRB_OK;
+}
+
+int swrb_timer_end(swrb_device* d, float* elapsed_ms) {
+    if (!d || !elapsed_ms) return fail(SWRB_E_INVALID, "null argument");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaEventRecord(d->timerEnd, d->stream));
+    CU(cudaEventSynchronize(d->timerEnd));
+    CU(cudaEventElapsedTime(elapsed_ms, d->timerBegin, d->timerEnd));
+    return check_overflow(d);
+}
+
+int swrb_flush_l2(swrb_device* d) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    if (!d->l2Scratch) {
+        d->l2ScratchBytes = (size_t)256 << 20;   // 2x the 126 MB L2
+        CU(cudaMalloc(&d->l2Scratch, d->l2ScratchBytes));
+    }
+    CU(cudaMemsetAsync(d->l2Scratch, 0x5A, d->l2ScratchBytes, d->stream));
+    return SWRB_OK;
+}
+
+int swrb_device_enable_stage_timing(swrb_device* d, int enable) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    if (enable && !d->st) {
+        d->st = new StageTimer();
+        memset(d->st->used, 0, sizeof(d->st->used));
+        for (int s = 0; s < SWRB_STAGE_COUNT_; s++)
+            for (int k = 0; k < 8; k++) { CU(cudaEventCreate(&d->st->begin[s][k])); CU(cudaEventCreate(&d->st->end[s][k])); }
+    }
+    d->stageTiming = enable != 0;
+    if (d->st) memset(d->st->used, 0, sizeof(d->st->used));
+    return SWRB_OK;
+}
+
+int swrb_get_stage_times(swrb_device* d, float out_us[SWRB_STAGE_COUNT_], uint32_t launches_out[SWRB_STAGE_COUNT_]) {
+    if (!d || !out_us) return fail(SWRB_E_INVALID, "null argument");
+    if (!d->st) return fail(SWRB_E_INVALID, "stage timing is not enabled");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));
+    for (int s = 0; s < SWRB_STAGE_COUNT_; s++) {
+        float total = 0;
+        for (uint32_t k = 0; k < d->st->used[s]; k++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, d->st->begin[s][k], d->st->end[s][k]));
+            total += ms;
+        }
+        out_us[s] = total * 1000.0f;
+        if (launches_out) launches_out[s] = d->st->used[s];
+    }
+    memset(d->st->used, 0, sizeof(d->st->used));
+    return check_overflow(d);
+}
+
+int swrb_get_launch_count(swrb_device* d, uint64_t* out) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    *out = d->launches;
+    return SWRB_OK;
+}
+
+}  // extern "C"

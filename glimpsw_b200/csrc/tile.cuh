@@ -1,0 +1,200 @@
+// tile.cuh — K3: the tile rasterizer of the binned path. One CTA owns one 32x32-px screen tile.
+//
+// Replaces Rasterizer::RasterizeBin (Rasterizer.cpp:696-739), TriangleEdgeVars::Setup (:296-329),
+// Rasterizer::DrawTriangle<> (Rasterizer.h:250-328) and FS_EncodeSurfaceId<false> (Shading.cpp:309-331).
+//
+// The tile's depth (and, implicitly, surface id) is staged in shared memory as 1024 64-bit
+// depth|id keys laid out exactly like the framebuffer's 4x4 fragments, so the epilogue is eight
+// 512-byte coalesced stores per layer. Triangles are taken from the tile's list 256 at a time:
+//   * a triangle whose pixel region inside the tile is small is rasterized by the thread that loaded it;
+//   * the others are queued in shared memory and rasterized one per warp: a coarse pass evaluates the
+//     tile's 32 8x4-px blocks at once (one block per lane, trivial reject per edge), then the warp
+//     visits each surviving block with one pixel per lane (fine test);
+//   * the frame's "big" triangles (more than kBigTriTileLimit tiles) are tested against the tile by
+//     all threads and join the same queue.
+// Depth resolution is an order-independent max on the keys (CAS on shared memory, almost always
+// skipped by a plain-load pre-check), which reproduces the reference's one-worker order.
+#pragma once
+
+#include "common.cuh"
+
+namespace swrb {
+
+constexpr int kTileThreads = 256;
+constexpr int kTileSmallArea = 32;   // pixels (inside the tile) a single thread rasterizes itself
+
+__device__ __forceinline__ void smem_key_max(unsigned long long* s, uint32_t off, unsigned long long key) {
+    unsigned long long cur = s[off];
+    while (key > cur) {
+        unsigned long long old = atomicCAS(&s[off], cur, key);
+        if (old == cur) break;
+        cur = old;
+    }
+}
+// index of pixel (lx, ly) of the tile in the fragment-tiled shared array
+__device__ __forceinline__ uint32_t tile_smem_index(uint32_t lx, uint32_t ly) {
+    return (ly >> 2) * 128u + (lx >> 2) * 16u + (ly & 3u) * 4u + (lx & 3u);
+}
+
+__device__ __forceinline__ TriRecord load_record(const TriRecord* tris, uint32_t i) {
+    const uint4* src = reinterpret_cast<const uint4*>(tris + i);
+    uint4 a = __ldg(src), b = __ldg(src + 1);
+    TriRecord t;
+    t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
+    t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
+    return t;
+}
+
+// Rasterize `t` into the tile with one thread (small regions).
+__device__ __forceinline__ void tile_raster_thread(const TriRecord& t, const BBox& r, const FrameParams& fp,
+                                                   int32_t tileX0, int32_t tileY0, unsigned long long* keys) {
+    Edges e;
+    edge_setup(t, fp.halfW, fp.halfH, e);
+    uint32_t rowE0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)r.minX + (uint32_t)e.b12 * (uint32_t)r.minY;
+    uint32_t rowE1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)r.minX + (uint32_t)e.b20 * (uint32_t)r.minY;
+    uint32_t rowE2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)r.minX + (uint32_t)e.b01 * (uint32_t)r.minY;
+    for (int32_t y = r.minY; y < r.maxY; y++) {
+        uint32_t e0 = rowE0, e1 = rowE1, e2 = rowE2;
+        for (int32_t x = r.minX; x < r.maxX; x++) {
+            if ((int32_t)(e0 | e1 | e2) >= 0) {
+                float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);
+                if (d > 0.0f) smem_key_max(keys, tile_smem_index((uint32_t)(x - tileX0), (uint32_t)(y - tileY0)), make_key(d, t.id));
+            }
+            e0 += (uint32_t)e.a12; e1 += (uint32_t)e.a20; e2 += (uint32_t)e.a01;
+        }
+        rowE0 += (uint32_t)e.b12; rowE1 += (uint32_t)e.b20; rowE2 += (uint32_t)e.b01;
+    }
+}
+
+// Rasterize `t` into the tile with one warp: coarse (32 blocks of 8x4 px) then fine.
+__device__ __forceinline__ void tile_raster_warp(const TriRecord& t, const FrameParams& fp, int32_t tileX0, int32_t tileY0,
+                                                 unsigned long long* keys) {
+    const uint32_t lane = lane_id();
+    BBox r;
+    raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r);
+    r.minX = max(r.minX, tileX0); r.minY = max(r.minY, tileY0);
+    r.maxX = min(r.maxX, tileX0 + kTileSize); r.maxY = min(r.maxY, tileY0 + kTileSize);
+    Edges e;
+    edge_setup(t, fp.halfW, fp.halfH, e);
+    const bool wrapFree = edges_wrap_free(t, e, fp);
+
+    // coarse: lane owns block (lane & 3, lane >> 2) of the tile's 4 x 8 grid of 8x4-px blocks
+    int32_t bxp = tileX0 + (int32_t)(lane & 3u) * 8, byp = tileY0 + (int32_t)(lane >> 2) * 4;
+    bool alive = bxp < r.maxX && bxp + 8 > r.minX && byp < r.maxY && byp + 4 > r.minY;
+    if (alive && wrapFree) {
+        int32_t v0 = e.e0 + e.a12 * bxp + e.b12 * byp;
+        int32_t v1 = e.e1 + e.a20 * bxp + e.b20 * byp;
+        int32_t v2 = e.e2 + e.a01 * bxp + e.b01 * byp;
+        v0 += (e.a12 > 0 ? e.a12 * 7 : 0) + (e.b12 > 0 ? e.b12 * 3 : 0);
+        v1 += (e.a20 > 0 ? e.a20 * 7 : 0) + (e.b20 > 0 ? e.b20 * 3 : 0);
+        v2 += (e.a01 > 0 ? e.a01 * 7 : 0) + (e.b01 > 0 ? e.b01 * 3 : 0);
+        alive = (v0 | v1 | v2) >= 0;
+    }
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, alive);
+    // fine: lane owns pixel (lane & 7, lane >> 3) of the current block
+    const uint32_t fx = lane & 7u, fy = lane >> 3;
+    while (todo) {
+        uint32_t blk = (uint32_t)__ffs(todo) - 1u;
+        todo &= todo - 1u;
+        int32_t px = tileX0 + (int32_t)((blk & 3u) * 8u + fx), py = tileY0 + (int32_t)((blk >> 2) * 4u + fy);
+        if (px >= r.minX && px < r.maxX && py >= r.minY && py < r.maxY) {
+            uint32_t e0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)px + (uint32_t)e.b12 * (uint32_t)py;
+            uint32_t e1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)px + (uint32_t)e.b20 * (uint32_t)py;
+            uint32_t e2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)px + (uint32_t)e.b01 * (uint32_t)py;
+            if ((int32_t)(e0 | e1 | e2) >= 0) {
+                float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);
+                if (d > 0.0f) smem_key_max(keys, tile_smem_index((uint32_t)(px - tileX0), (uint32_t)(py - tileY0)), make_key(d, t.id));
+            }
+        }
+    }
+}
+
+// clearMode: 0 = load the tile's depth from the framebuffer; 1 = framebuffer is freshly cleared to
+// (clearColor, clearDepthBits) and this kernel performs the clear for the tile as part of its store.
+__global__ void __launch_bounds__(kTileThreads)
+k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ tileOffset,
+              const uint32_t* __restrict__ binEntries, const uint32_t* __restrict__ bigList, FrameParams fp,
+              uint32_t* __restrict__ colorLayer, uint32_t* __restrict__ depthLayer,
+              int clearMode, uint32_t clearColor, uint32_t clearDepthBits, DevCtl* __restrict__ ctl) {
+    __shared__ __align__(16) unsigned long long keys[kTilePixels];
+    __shared__ uint32_t wideList[kTileThreads];
+    __shared__ uint32_t wideCount;
+
+    if (ctl->overflow) return;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t tx = tile % fp.tilesX, ty = tile / fp.tilesX;
+    const int32_t tileX0 = (int32_t)(tx << kTileShift), tileY0 = (int32_t)(ty << kTileShift);
+    const uint32_t listBegin = tileOffset[tile], listEnd = tileOffset[tile + 1];
+    const uint32_t numBig = ctl->bigCount;
+    if (clearMode == 0 && listBegin == listEnd && numBig == 0) return;   // nothing can change in this tile
+
+    // ---- stage the tile: thread owns 4 consecutive pixels (one row of a 4x4 fragment)
+    const uint32_t fr = tid >> 5, l4 = (tid & 31u) * 4u;                 // fragment row, first of 4 pixels in it
+    const uint32_t gx = (uint32_t)tileX0 + (l4 >> 4) * 4u, gy = (uint32_t)tileY0 + fr * 4u + ((l4 >> 2) & 3u);
+    const bool inFb = gx < fp.width && gy < fp.height;
+    const uint32_t gOff = fb_pixel_offset(gx, gy, fp.width);
+    {
+        uint4 d = make_uint4(clearDepthBits, clearDepthBits, clearDepthBits, clearDepthBits);
+        if (clearMode == 0 && inFb) d = *reinterpret_cast<const uint4*>(depthLayer + gOff);
+        unsigned long long* k = keys + fr * 128u + l4;
+        k[0] = ((unsigned long long)d.x << 32) | kKeySeed;
+        k[1] = ((unsigned long long)d.y << 32) | kKeySeed;
+        k[2] = ((unsigned long long)d.z << 32) | kKeySeed;
+        k[3] = ((unsigned long long)d.w << 32) | kKeySeed;
+    }
+    if (tid == 0) wideCount = 0;
+    __syncthreads();
+
+    // ---- triangles: the tile's list, then the frame's big list
+    const uint32_t total = (listEnd - listBegin) + numBig;
+    for (uint32_t base = 0; base < total; base += kTileThreads) {
+        uint32_t j = base + tid;
+        if (j < total) {
+            uint32_t triIdx = j < (listEnd - listBegin) ? binEntries[listBegin + j] : bigList[j - (listEnd - listBegin)];
+            TriRecord t = load_record(tris, triIdx);
+            BBox r;
+            if (raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) {
+                r.minX = max(r.minX, tileX0); r.minY = max(r.minY, tileY0);
+                r.maxX = min(r.maxX, tileX0 + kTileSize); r.maxY = min(r.maxY, tileY0 + kTileSize);
+                int32_t w = r.maxX - r.minX, h = r.maxY - r.minY;
+                if (w > 0 && h > 0) {
+                    if (w * h <= kTileSmallArea) tile_raster_thread(t, r, fp, tileX0, tileY0, keys);
+                    else wideList[atomicAdd(&wideCount, 1u)] = triIdx;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nWide = wideCount;
+        for (uint32_t w = tid >> 5; w < nWide; w += kTileThreads / 32) {
+            TriRecord t = load_record(tris, wideList[w]);
+            tile_raster_warp(t, fp, tileX0, tileY0, keys);
+        }
+        __syncthreads();
+        if (tid == 0) wideCount = 0;
+        __syncthreads();
+    }
+
+    // ---- epilogue: 128-bit coalesced stores in the framebuffer's own 4x4-tiled order
+    if (inFb) {
+        const unsigned long long* k = keys + fr * 128u + l4;
+        unsigned long long k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
+        uint32_t l0 = (uint32_t)k0, l1 = (uint32_t)k1, l2 = (uint32_t)k2, l3 = (uint32_t)k3;
+        bool anyWon = (l0 & l1 & l2 & l3) != kKeySeed;
+        if (anyWon || clearMode == 1) {
+            uint4 d = make_uint4((uint32_t)(k0 >> 32), (uint32_t)(k1 >> 32), (uint32_t)(k2 >> 32), (uint32_t)(k3 >> 32));
+            uint4 c = make_uint4(clearColor, clearColor, clearColor, clearColor);
+            bool allWon = l0 != kKeySeed && l1 != kKeySeed && l2 != kKeySeed && l3 != kKeySeed;
+            if (clearMode == 0 && !allWon) c = *reinterpret_cast<const uint4*>(colorLayer + gOff);
+            if (l0 != kKeySeed) c.x = kKeyIdBase - l0;
+            if (l1 != kKeySeed) c.y = kKeyIdBase - l1;
+            if (l2 != kKeySeed) c.z = kKeyIdBase - l2;
+            if (l3 != kKeySeed) c.w = kKeyIdBase - l3;
+            *reinterpret_cast<uint4*>(depthLayer + gOff) = d;
+            *reinterpret_cast<uint4*>(colorLayer + gOff) = c;
+        }
+    }
+    if (tid == 0 && listBegin != listEnd) atomicAdd(&ctl->perf[3], 1ull);   // BinQueueFlushes (Rasterizer.cpp:622)
+}
+
+}  // namespace swrb

@@ -1,0 +1,151 @@
+/* swrb.h — C ABI of the B200-native meshlet raster path (libswrb.so).
+ *
+ * This is the drop-in boundary for ONE path of GLimpSW: meshlet cull -> mesh shade ->
+ * triangle setup -> bin -> tile raster -> vis-buffer -> resolve. Each entry point names
+ * the reference interface it replaces (paths relative to /root/reference/). Plain
+ * pointers and sizes only; no C++/torch types. All functions return 0 on success or a
+ * negative swrb_status; swrb_last_error() gives a thread-local message. Nothing here
+ * has a CPU fallback: without a CUDA device every call fails with SWRB_E_CUDA.
+ *
+ * Threading (Rasterizer.cpp:852 — the reference Rasterizer is single-caller): one
+ * swrb_device = one CUDA device + one stream; calls enqueue asynchronously on that
+ * stream; swrb_sync() and the download calls synchronise. Use one device object per GPU.
+ */
+#ifndef SWRB_H
+#define SWRB_H
+
+#include "swr_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SWRB_API
+#else
+#define SWRB_API __attribute__((visibility("default")))
+#endif
+
+typedef enum swrb_status {
+    SWRB_OK = 0,
+    SWRB_E_INVALID = -1,       /* bad argument (null handle, w/h not multiple of 4, > 2896, ...) */
+    SWRB_E_CUDA = -2,          /* CUDA runtime error, message in swrb_last_error() */
+    SWRB_E_OOM = -3,
+    SWRB_E_BIN_OVERFLOW = -4,  /* device-side work list overflowed; nothing was dropped silently:
+                                  the draw was aborted before touching the framebuffer */
+    SWRB_E_UNSUPPORTED = -5
+} swrb_status;
+
+typedef struct swrb_device swrb_device;
+typedef struct swrb_scene swrb_scene;
+typedef struct swrb_fb swrb_fb;
+
+/* Rasterizer public toggles — Rasterizer.h:206-208 */
+enum {
+    SWRB_FLAG_BINNING   = 1u << 0,  /* EnableBinning: screen-tile binner + shared-memory tile raster.
+                                       Off = direct path (per-triangle 64-bit atomicMax into HBM keys). */
+    SWRB_FLAG_CLIPPING  = 1u << 1,  /* EnableClipping (only meaningful with binning off, Rasterizer.cpp:209) */
+    SWRB_FLAG_GUARDBAND = 1u << 2,  /* EnableGuardband (ignored by the binned path, Rasterizer.cpp:509) */
+    SWRB_FLAG_FUSED_FRUSTUM_CULL = 1u << 3, /* evaluate CullMeshlets' frustum test inside the mesh kernel
+                                               (planes from swrb_draw_desc.FrustumPlanes) */
+    SWRB_FLAGS_DEFAULT = SWRB_FLAG_BINNING | SWRB_FLAG_CLIPPING | SWRB_FLAG_GUARDBAND
+};
+
+/* One DrawMeshlets call: Rasterizer::DrawMeshlets(fb, count, {VisBufferShader, &ctx})
+ * (Rasterizer.h:213, Main.cpp:236-240) with the ShadingContext per-instance uniforms
+ * (Shading.h:21-26) it reads. */
+typedef struct swrb_draw_desc {
+    uint32_t MeshletOffset;        /* ShadingContext::MeshletOffset */
+    uint32_t MeshletCount;         /* `count` */
+    float    ObjectToClip[16];     /* ShadingContext::ObjectToClipMat, column-major (glm::mat4) */
+    const uint16_t* CullBitmapHost;/* ShadingContext::MeshletCullBitmap (host, 1 bit/meshlet) or NULL */
+    int32_t  UseDeviceCullBitmap;  /* 1: use the bitmap the last swrb_cull_meshlets left on the device */
+    float    FrustumPlanes[5][4];  /* only read with SWRB_FLAG_FUSED_FRUSTUM_CULL */
+} swrb_draw_desc;
+
+/* ShadingContext resolve-pass uniforms — Shading.h:21-33 */
+typedef struct swrb_shading_uniforms {
+    float WorldToClip[16];         /* column-major */
+    float ObjectToClip[16];
+    float ObjectToWorld[9];        /* glm::mat3, column-major */
+    float InvScreenProj[16];       /* GetInverseScreenProjMatrix(WorldToClip, size) (Camera.h:140-146), host-computed */
+    float ViewPos[3];
+    float Exposure;
+} swrb_shading_uniforms;
+
+/* ---- device ------------------------------------------------------------------------ */
+SWRB_API int swrb_device_create(int cuda_device, swrb_device** out);   /* Rasterizer::Rasterizer (Rasterizer.cpp:125) */
+SWRB_API void swrb_device_destroy(swrb_device* dev);
+SWRB_API int swrb_device_set_stream(swrb_device* dev, void* cuda_stream); /* borrow an external cudaStream_t (NULL = own) */
+SWRB_API int swrb_device_set_flags(swrb_device* dev, uint32_t flags);  /* EnableBinning/Clipping/Guardband */
+SWRB_API int swrb_device_reserve(swrb_device* dev, uint64_t max_triangles, uint64_t max_bin_entries);
+SWRB_API int swrb_sync(swrb_device* dev);
+SWRB_API const char* swrb_last_error(void);
+SWRB_API const char* swrb_version(void);
+
+/* perf::GetCurrent / perf::Reset (Rasterizer.h:381-395). Integer counters come from device atomics. */
+SWRB_API int swrb_get_counters(swrb_device* dev, uint64_t out[SWR_PERF_Count_]);
+SWRB_API int swrb_reset_counters(swrb_device* dev);
+
+/* ---- scene (Scene::Meshlets/Materials/Textures/Lights, Scene.h:117-123) -------------- */
+SWRB_API int swrb_scene_create(swrb_device* dev,
+                               const swr_meshlet* meshlets, uint32_t num_meshlets,
+                               const swr_material* materials, uint32_t num_materials,
+                               const swr_texture_desc* textures, uint32_t num_textures,
+                               const swr_light* lights, uint32_t num_lights,
+                               swrb_scene** out);
+SWRB_API int swrb_scene_update_meshlets(swrb_scene* scene, const swr_meshlet* meshlets, uint32_t first, uint32_t count);
+SWRB_API void swrb_scene_destroy(swrb_scene* scene);
+
+/* ---- framebuffer (CreateFramebuffer Rasterizer.h:66-78; Clear/ClearLayer :35-48;
+ *      GetPixels ImageHelpers.cpp:109-147) -------------------------------------------- */
+SWRB_API int swrb_fb_create(swrb_device* dev, uint32_t width, uint32_t height, uint32_t num_layers, swrb_fb** out);
+SWRB_API void swrb_fb_destroy(swrb_fb* fb);
+SWRB_API int swrb_fb_info(const swrb_fb* fb, swr_fb_info* out);
+SWRB_API int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth);
+SWRB_API int swrb_fb_clear_layer(swrb_fb* fb, uint32_t layer, uint32_t value);
+SWRB_API int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host);  /* raw GetLayerData copy */
+SWRB_API int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host);
+SWRB_API int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride); /* Framebuffer::GetPixels */
+SWRB_API int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride); /* same, device dst */
+
+/* ---- hot path ------------------------------------------------------------------------ */
+/* ShadingContext::CullMeshlets frustum part (Shading.cpp:775-809, :865-867). Planes are
+ * derived on the host from P,V,M exactly as the reference does; depth_pyramid must be NULL
+ * (HiZ is a later row). Writes 1 bit/meshlet to bitmap_out_host (if non-NULL, ceil(count/16)
+ * uint16) and keeps a device copy for UseDeviceCullBitmap. Returns the visible count. */
+SWRB_API int swrb_cull_meshlets(swrb_scene* scene, uint32_t meshlet_offset, uint32_t count,
+                                const float proj[16], const float view[16], const float model[16],
+                                uint16_t* bitmap_out_host, uint32_t* visible_out);
+/* The five normalised Gribb-Hartmann planes CullMeshlets tests (Shading.cpp:783-791, :806). */
+SWRB_API int swrb_frustum_planes(const float proj[16], const float view[16], const float model[16], float planes_out[5][4]);
+
+/* Rasterizer::DrawMeshlets with the VisBufferShader table (mesh program = ShadeMeshlet
+ * Shading.cpp:281-307; fragment programs = FS_EncodeSurfaceId<false/true> :309-331). */
+SWRB_API int swrb_draw_meshlets(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draw);
+/* Several DrawMeshlets calls (one per glTF node, Main.cpp:216-240) submitted as one batch.
+ * Results equal issuing them one after another when MeshletOffset is non-decreasing. */
+SWRB_API int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws);
+/* Literal drop-in form: ctx.Meshlets is a HOST pointer, uploaded on every call. */
+SWRB_API int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint32_t count,
+                                     const float object_to_clip[16], const uint16_t* cull_bitmap_host);
+
+/* ShadingContext::Resolve (Shading.cpp:658-689): overwrites layer 0 with RGBA8 colour. */
+SWRB_API int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* uniforms);
+
+/* ---- timing helpers (CUDA events on the device's stream; used by bench.py) ------------- */
+SWRB_API int swrb_timer_begin(swrb_device* dev);
+SWRB_API int swrb_timer_end(swrb_device* dev, float* elapsed_ms);    /* synchronises */
+SWRB_API int swrb_flush_l2(swrb_device* dev);                          /* writes a >L2-sized scratch buffer */
+/* Per-stage device time of the last frame in microseconds (stage ids below); needs
+ * swrb_device_enable_stage_timing(dev,1), which inserts events around every kernel. */
+enum { SWRB_STAGE_CLEAR = 0, SWRB_STAGE_CULL, SWRB_STAGE_MESH, SWRB_STAGE_BIN, SWRB_STAGE_RASTER,
+       SWRB_STAGE_RESOLVE, SWRB_STAGE_COUNT_ };
+SWRB_API int swrb_device_enable_stage_timing(swrb_device* dev, int enable);
+SWRB_API int swrb_get_stage_times(swrb_device* dev, float out_us[SWRB_STAGE_COUNT_], uint32_t launches_out[SWRB_STAGE_COUNT_]);
+SWRB_API int swrb_get_launch_count(swrb_device* dev, uint64_t* out);  /* kernels launched since create */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWRB_H */

@@ -1,0 +1,372 @@
+// oracle.cpp — CPU restatement of GLimpSW's meshlet raster path (vis-buffer half).
+//
+// TEST INFRASTRUCTURE ONLY. Nothing under glimpsw_b200/ may import, link or execute
+// this file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs can check and time the reference algorithm on the host.
+//
+// PARITY UNPINNED: the reference ships no tests, golden images or known-answer vectors
+// for this path and cannot be compiled in this image (it needs clang
+// vector extensions, _BitInt and CPM-fetched glm/meshoptimizer/stb; only g++ is present).
+// This file is therefore a line-by-line restatement of the reference SOURCE, each function
+// citing the file:line it follows (paths relative to /root/reference/), in the canonical
+// arithmetic of SURVEY.md Appendix A: IEEE-754 binary32 round-to-nearest-even, an FMA
+// exactly where the source writes simd::fma / simd::mul / simd::dot, separately rounded
+// * + - elsewhere, correctly rounded '/', float->int by RNE (vcvtps2dq), wrapping int32.
+// (The upstream build uses -ffast-math, under which clang may turn 1.0f/x into
+// vrcp14ps+Newton; that is not reproducible off x86 — SURVEY.md App. B.1.)
+//
+// Build: g++ -O2 -march=x86-64-v3 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
+// Scalar on purpose: this file is the spec. oracle/baseline_mt.cpp is the threaded
+// restatement used as the timed CPU baseline, and must equal this file bit for bit.
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cfenv>
+
+#include "../include/swr_types.h"
+
+namespace {
+
+// ---- SIMD.h op semantics -------------------------------------------------------------
+inline int32_t round2i(float x) {  // SIMD.h:304 (_mm512_cvtps_epi32: RNE, 0x80000000 on overflow/NaN)
+    if (!(x > -2147483904.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)std::nearbyintf(x);  // default rounding mode = nearest-even
+}
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+struct Vec4 { float x, y, z, w; };
+
+// simd::mul(mat4, v4) with v.w == 1 — SIMD.h:457-464. m is column-major (glm): m[c*4+r].
+inline Vec4 mul_mat4_pos(const float* m, float x, float y, float z) {
+    Vec4 r;
+    r.x = std::fmaf(x, m[0 * 4 + 0], std::fmaf(y, m[1 * 4 + 0], std::fmaf(z, m[2 * 4 + 0], 1.0f * m[3 * 4 + 0])));
+    r.y = std::fmaf(x, m[0 * 4 + 1], std::fmaf(y, m[1 * 4 + 1], std::fmaf(z, m[2 * 4 + 1], 1.0f * m[3 * 4 + 1])));
+    r.z = std::fmaf(x, m[0 * 4 + 2], std::fmaf(y, m[1 * 4 + 2], std::fmaf(z, m[2 * 4 + 2], 1.0f * m[3 * 4 + 2])));
+    r.w = std::fmaf(x, m[0 * 4 + 3], std::fmaf(y, m[1 * 4 + 3], std::fmaf(z, m[2 * 4 + 3], 1.0f * m[3 * 4 + 3])));
+    return r;
+}
+// simd::perspective_div — SIMD.h:473-476
+inline Vec4 perspective_div(Vec4 v) {
+    float rw = 1.0f / v.w;
+    return { v.x * rw, v.y * rw, v.z * rw, rw };
+}
+
+inline int16_t lo16(uint32_t p) { return (int16_t)(p & 0xFFFF); }
+inline int16_t hi16(uint32_t p) { return (int16_t)(p >> 16); }
+inline uint32_t pack16(int16_t lo, int16_t hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
+inline int16_t min16(int16_t a, int16_t b) { return a < b ? a : b; }
+inline int16_t max16(int16_t a, int16_t b) { return a > b ? a : b; }
+// per-s16 helpers on packed pairs (vpminsw / vpmaxsw / vpsraw / vpaddw)
+inline uint32_t pmin16(uint32_t a, uint32_t b) { return pack16(min16(lo16(a), lo16(b)), min16(hi16(a), hi16(b))); }
+inline uint32_t pmax16(uint32_t a, uint32_t b) { return pack16(max16(lo16(a), lo16(b)), max16(hi16(a), hi16(b))); }
+inline uint32_t psra16(uint32_t a, int s) { return pack16((int16_t)(lo16(a) >> s), (int16_t)(hi16(a) >> s)); }
+inline uint32_t padd16(uint32_t a, uint32_t b) { return pack16((int16_t)(lo16(a) + lo16(b)), (int16_t)(hi16(a) + hi16(b))); }
+
+// ---- Triangle setup ------------------------------------------------------------------
+struct TriSetup {           // one lane of TrianglePacket (Rasterizer.h:145-161)
+    uint32_t Pos0, Pos1, Pos2;
+    float Z0, Z1, Z2, W0, W1, W2;
+};
+struct TriEdges {           // one lane of TriangleEdgeVars (Rasterizer.h:162-176)
+    int32_t Edge0, Edge1, Edge2, A01, A12, A20, B01, B12, B20;
+    float Z0, Z10, Z20, W0, W0S, W1S, W2S;
+};
+
+// TrianglePacket::GetBoundingBox + GetRenderBoundingBox — Rasterizer.cpp:331-351
+inline void render_bbox(const TriSetup& t, int halfW, int halfH, uint32_t& bbMin, uint32_t& bbMax) {
+    uint32_t minPos = pmin16(pmin16(t.Pos0, t.Pos1), t.Pos2);
+    uint32_t maxPos = pmax16(pmax16(t.Pos0, t.Pos1), t.Pos2);
+    // :335-336 — a 32-bit add on packed s16 pairs (the carry from x into y is intended to be replicated)
+    minPos = psra16(minPos + 0x00070007u, 4);
+    maxPos = psra16(maxPos + 0x00070007u, 4);
+    uint32_t vpSize = (uint32_t)halfW | ((uint32_t)halfH << 16);            // :343
+    minPos = pmin16(pmax16(padd16(minPos, vpSize), 0), vpSize * 2);          // :344
+    maxPos = pmin16(pmax16(padd16(maxPos, vpSize), 0), vpSize * 2);          // :345
+    bbMin = (minPos + 0x00000000u) & ~0x00030003u;                           // :347
+    bbMax = (maxPos + 0x00030003u) & ~0x00030003u;                           // :348
+}
+
+// TrianglePacket::Setup for one lane — Rasterizer.cpp:257-289. Returns 1 if the lane survives.
+inline int tri_setup(Vec4 v0, Vec4 v1, Vec4 v2, int halfW, int halfH, int cullMode, TriSetup& out) {
+    v0 = perspective_div(v0);
+    v1 = perspective_div(v1);
+    v2 = perspective_div(v2);
+
+    // :262 (canonical: every product rounded, then the subtraction)
+    float det = (v2.x - v0.x) * (v1.y - v0.y) - (v0.x - v1.x) * (v0.y - v2.y);
+    if (cullMode != SWR_CULL_FRONT_CCW) {                                    // :264-267
+        bool flip = (cullMode == SWR_CULL_FRONT_CW) ? true : (det < 0);
+        det = flip ? -det : det;
+    }
+    int keep = det > 0;                                                      // :269
+
+    float fixX = (float)(halfW * 16), fixY = (float)(halfH * 16);            // :272
+    int32_t x0 = round2i(v0.x * fixX), y0 = round2i(v0.y * fixY);
+    int32_t x1 = round2i(v1.x * fixX), y1 = round2i(v1.y * fixY);
+    int32_t x2 = round2i(v2.x * fixX), y2 = round2i(v2.y * fixY);
+    out.Pos0 = ((uint32_t)x0 & 0xFFFF) | ((uint32_t)y0 << 16);               // :277-279
+    out.Pos1 = ((uint32_t)x1 & 0xFFFF) | ((uint32_t)y1 << 16);
+    out.Pos2 = ((uint32_t)x2 & 0xFFFF) | ((uint32_t)y2 << 16);
+
+    uint32_t bbMin, bbMax;
+    render_bbox(out, halfW, halfH, bbMin, bbMax);
+    // :283 — drop when minX >= maxX or minY >= maxY (signed 16-bit compares)
+    if (lo16(bbMin) >= lo16(bbMax) || hi16(bbMin) >= hi16(bbMax)) keep = 0;
+
+    out.Z0 = v0.z; out.Z1 = v1.z; out.Z2 = v2.z;                             // :285-286
+    out.W0 = v0.w; out.W1 = v1.w; out.W2 = v2.w;
+    return keep;
+}
+
+// ComputeEdge — Rasterizer.cpp:291-295 (wrapping 32-bit arithmetic, arithmetic shift)
+inline int32_t compute_edge(int32_t a, int32_t x, int32_t b, int32_t y) {
+    uint32_t w = (uint32_t)a * (uint32_t)x + (uint32_t)b * (uint32_t)y;
+    w += (a > 0 || (a == 0 && b > 0)) ? 0u : 0xFFFFFFFFu;
+    return (int32_t)w >> 4;
+}
+// TriangleEdgeVars::Setup for one lane — Rasterizer.cpp:296-329
+inline void edge_setup(const TriSetup& t, int halfW, int halfH, TriEdges& e) {
+    int32_t x0 = lo16(t.Pos0), y0 = hi16(t.Pos0);
+    int32_t x1 = lo16(t.Pos1), y1 = hi16(t.Pos1);
+    int32_t x2 = lo16(t.Pos2), y2 = hi16(t.Pos2);
+    e.A01 = y1 - y0; e.B01 = x0 - x1;
+    e.A12 = y2 - y1; e.B12 = x1 - x2;
+    e.A20 = y0 - y2; e.B20 = x2 - x0;
+    int32_t det = (int32_t)((uint32_t)e.B20 * (uint32_t)e.A01 - (uint32_t)e.B01 * (uint32_t)e.A20);
+    if (det < 0) {
+        e.A01 = -e.A01; e.B01 = -e.B01; e.A12 = -e.A12; e.B12 = -e.B12; e.A20 = -e.A20; e.B20 = -e.B20;
+        det = (int32_t)(0u - (uint32_t)det);
+    }
+    int32_t sampleX = (int32_t)((uint32_t)(-halfW) << 4) + 8, sampleY = (int32_t)((uint32_t)(-halfH) << 4) + 8;  // :315
+    e.Edge0 = compute_edge(e.A12, sampleX - x1, e.B12, sampleY - y1);
+    e.Edge1 = compute_edge(e.A20, sampleX - x2, e.B20, sampleY - y2);
+    e.Edge2 = compute_edge(e.A01, sampleX - x0, e.B01, sampleY - y0);
+
+    float rcpArea = 16.0f / (float)det;                                       // :320
+    e.Z0 = t.Z0;
+    e.Z10 = (t.Z1 - t.Z0) * rcpArea;
+    e.Z20 = (t.Z2 - t.Z0) * rcpArea;
+    e.W0 = t.W0;
+    e.W0S = t.W0 * rcpArea; e.W1S = t.W1 * rcpArea; e.W2S = t.W2 * rcpArea;
+}
+
+// Clipper::ComputeClipCodes for one lane — Rasterizer.cpp:353-397.
+// returns bit0 = accept, bit1 = non-trivial; *outcodes = partial outcodes
+inline int clip_codes(const Vec4 v[3], float bx, float by, uint8_t* outcodes) {
+    uint8_t partial = 0, combined = 255;
+    bool trivial = true;
+    for (int i = 0; i < 3; i++) {
+        const Vec4& vi = v[i];
+        uint8_t oc = 0;
+        if (vi.x < -vi.w) oc |= 1 << 0;   // Left
+        if (vi.x > +vi.w) oc |= 1 << 1;   // Right
+        if (vi.y < -vi.w) oc |= 1 << 2;   // Top
+        if (vi.y > +vi.w) oc |= 1 << 3;   // Bottom
+        if (vi.z < -vi.w) oc |= 1 << 4;   // Near
+        if (vi.z > +vi.w) oc |= 1 << 5;   // Far
+        partial |= oc;
+        combined &= oc;
+        trivial = trivial && (std::fabs(vi.x) < vi.w * bx && std::fabs(vi.y) < vi.w * by);   // :386
+    }
+    trivial = trivial && ((partial & ((1 << 4) | (1 << 5))) == 0);                           // :388
+    bool visible = combined == 0;                                                             // :389
+    if (outcodes) *outcodes = partial;
+    return (visible && trivial ? 1 : 0) | (visible && !trivial ? 2 : 0);
+}
+
+inline uint32_t fb_pixel_offset(uint32_t x, uint32_t y, uint32_t width) {   // Rasterizer.h:50-56
+    return ((x & ~3u) << 2) + (y & ~3u) * width + (x & 3) + (y & 3) * 4;
+}
+
+// Rasterizer::DrawTriangle<FS_EncodeSurfaceId<false>, false> — Rasterizer.h:250-328 + Shading.cpp:309-331,
+// written per pixel: the reference walks 4x4 fragments over [bbMin, bbMax) and tests sign(e0|e1|e2).
+inline void draw_triangle(uint32_t* color, float* depth, uint32_t width, const TriEdges& e,
+                          uint32_t bbMin, uint32_t bbMax, uint32_t surfaceId) {
+    uint32_t minX = bbMin & 0xFFFF, minY = bbMin >> 16, maxX = bbMax & 0xFFFF, maxY = bbMax >> 16;
+    for (uint32_t y = minY; y < maxY; y++) {
+        for (uint32_t x = minX; x < maxX; x++) {
+            uint32_t e0 = (uint32_t)e.Edge0 + (uint32_t)e.A12 * x + (uint32_t)e.B12 * y;
+            uint32_t e1 = (uint32_t)e.Edge1 + (uint32_t)e.A20 * x + (uint32_t)e.B20 * y;
+            uint32_t e2 = (uint32_t)e.Edge2 + (uint32_t)e.A01 * x + (uint32_t)e.B01 * y;
+            if ((int32_t)(e0 | e1 | e2) < 0) continue;                       // Rasterizer.h:289-290
+            float u = (float)(int32_t)e1, v = (float)(int32_t)e2;            // :293-294
+            float d = std::fmaf(u, e.Z10, std::fmaf(v, e.Z20, e.Z0));        // :296
+            uint32_t off = fb_pixel_offset(x, y, width);
+            if (d > depth[off]) {                                            // Shading.cpp:311-313
+                depth[off] = d;                                              // :329
+                color[off] = surfaceId;                                      // :328,:330
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ShadeMeshlet — Shading.cpp:281-307. cullBitmap may be NULL. `index` is the meshlet index
+// within the draw; meshlets points at element MeshletOffset already.
+// Returns PrimCount. Canonical rule for material-less meshlets: FrontCCW, FS 0.
+int orc_shade_meshlet(const swr_meshlet* meshlets, uint32_t index, const uint16_t* cullBitmap,
+                      const float* objectToClip, const swr_material* materials, swr_shaded_meshlet* out) {
+    out->PrimCount = 0;
+    out->CullMode = SWR_CULL_FRONT_CCW;
+    out->FragmentShaderId = 0;
+    if (cullBitmap != nullptr) {
+        uint16_t mask = cullBitmap[index / 16];
+        if (((mask >> (index % 16)) & 1) == 0) return 0;
+    }
+    const swr_meshlet& mesh = meshlets[index];
+    uint32_t nv = (mesh.NumVertices + 15u) & ~15u;   // the reference walks 16-wide vectors (:295)
+    if (nv > 64) nv = 64;
+    for (uint32_t i = 0; i < nv; i++) {
+        Vec4 c = mul_mat4_pos(objectToClip, mesh.Positions[0][i], mesh.Positions[1][i], mesh.Positions[2][i]);
+        out->Position[0][i] = c.x; out->Position[1][i] = c.y; out->Position[2][i] = c.z; out->Position[3][i] = c.w;
+    }
+    out->PrimCount = mesh.NumTriangles;
+    memcpy(out->Indices, mesh.Indices, sizeof(mesh.Indices));
+    if (mesh.MaterialId != SWR_NO_MATERIAL && materials != nullptr) {
+        const swr_material& mat = materials[mesh.MaterialId];
+        out->CullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
+        out->FragmentShaderId = mat.AlphaCutoff < 255 ? 1 : 0;
+    }
+    return out->PrimCount;
+}
+
+// Single-triangle probes for known-answer tests ------------------------------------------
+// clip-space verts v[3][4]; returns accept bits (bit0 accept, bit1 nontrivial) in *cc, the lane-survives flag
+// as return value; packed positions, render bbox and edge equations in out arrays.
+int orc_probe_triangle(const float* v, uint32_t width, uint32_t height, int cullMode, int guardband,
+                       int* cc, uint32_t pos[3], uint32_t bbox[2], int32_t edges[9], float zw[7]) {
+    Vec4 vv[3];
+    for (int i = 0; i < 3; i++) vv[i] = { v[i * 4 + 0], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3] };
+    float bx = guardband ? (float)SWR_MAX_RENDER_SIZE / (float)width : 1.0f;
+    float by = guardband ? (float)SWR_MAX_RENDER_SIZE / (float)height : 1.0f;
+    *cc = clip_codes(vv, bx, by, nullptr);
+    TriSetup t;
+    int keep = tri_setup(vv[0], vv[1], vv[2], (int)width / 2, (int)height / 2, cullMode, t);
+    pos[0] = t.Pos0; pos[1] = t.Pos1; pos[2] = t.Pos2;
+    render_bbox(t, (int)width / 2, (int)height / 2, bbox[0], bbox[1]);
+    TriEdges e;
+    edge_setup(t, (int)width / 2, (int)height / 2, e);
+    int32_t ee[9] = { e.Edge0, e.Edge1, e.Edge2, e.A12, e.A20, e.A01, e.B12, e.B20, e.B01 };
+    memcpy(edges, ee, sizeof(ee));
+    float f[7] = { e.Z0, e.Z10, e.Z20, e.W0, e.W0S, e.W1S, e.W2S };
+    memcpy(zw, f, sizeof(f));
+    return keep;
+}
+
+// Rasterizer::DrawMeshlets (binned semantics: Rasterizer.cpp:493-644 with 1 worker, i.e. meshlet-ascending,
+// primitive-ascending order; non-trivial triangles are counted then dropped :567-569) with the
+// VisBufferShader table, opaque fragment program only.
+//   color/depth : layer 0 / layer 1 of a 4x4-tiled framebuffer (Rasterizer.h:10-63)
+//   meshlets    : scene base pointer; the draw covers [meshletOffset, meshletOffset+count)
+//   flags bit0  : guard band enabled (the binned path always enables it, Rasterizer.cpp:509)
+//   counters[4] : TrianglesProcessed, TrianglesRasterized, TrianglesClipped, (unused) — accumulated
+// Alpha-tested materials (FragmentShaderId 1) are drawn with the opaque program here; the alpha
+// variant lives in oracle_resolve.cpp because it needs the texture sampler.
+void orc_draw_meshlets(uint32_t* color, float* depth, uint32_t width, uint32_t height,
+                       const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                       const float* objectToClip, const uint16_t* cullBitmap,
+                       const swr_material* materials, uint32_t flags, uint64_t* counters) {
+    int halfW = (int)width / 2, halfH = (int)height / 2;                                   // :508
+    float bx = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)width : 1.0f;             // :509
+    float by = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)height : 1.0f;
+    static swr_shaded_meshlet mesh;   // (single-threaded test oracle)
+
+    for (uint32_t meshIdx = 0; meshIdx < count; meshIdx++) {
+        if (orc_shade_meshlet(meshlets + meshletOffset, meshIdx, cullBitmap, objectToClip, materials, &mesh) == 0) continue;
+        counters[0] += mesh.PrimCount;                                                     // :545
+
+        for (uint32_t prim = 0; prim < mesh.PrimCount; prim++) {                           // lanes of :550-594
+            Vec4 v[3];
+            for (int k = 0; k < 3; k++) {
+                uint32_t idx = mesh.Indices[k][prim] & 63;                                 // 64-entry permute (SIMD.h:219-230)
+                v[k] = { mesh.Position[0][idx], mesh.Position[1][idx], mesh.Position[2][idx], mesh.Position[3][idx] };
+            }
+            int cc = clip_codes(v, bx, by, nullptr);
+            if (cc & 2) counters[2] += 1;                                                  // :567-569
+            if (!(cc & 1)) continue;
+            TriSetup t;
+            if (!tri_setup(v[0], v[1], v[2], halfW, halfH, mesh.CullMode, t)) continue;    // :574-577
+            counters[1] += 1;                                                              // :579
+
+            uint32_t bbMin, bbMax;
+            render_bbox(t, halfW, halfH, bbMin, bbMax);                                    // :588 / :714
+            TriEdges e;
+            edge_setup(t, halfW, halfH, e);                                                // :721
+            uint32_t surfaceId = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;         // Shading.cpp:328
+            draw_triangle(color, depth, width, e, bbMin, bbMax, surfaceId);
+        }
+    }
+}
+
+// Framebuffer::GetPixels — ImageHelpers.cpp:109-147 (de-tile one layer into row-major)
+void orc_fb_get_pixels(const uint32_t* layer, uint32_t width, uint32_t height, uint32_t* dest, uint32_t stride) {
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++) dest[y * stride + x] = layer[fb_pixel_offset(x, y, width)];
+}
+
+// glm helpers needed by CullMeshlets' host-side plane derivation (glm 1.0.1 scalar code paths:
+// mat4*mat4 is four column combinations a0*b0 + a1*b1 + a2*b2 + a3*b3 evaluated left to right).
+static void mat4_mul(const float* a, const float* b, float* r) {
+    float t[16];
+    for (int c = 0; c < 4; c++)
+        for (int k = 0; k < 4; k++)
+            t[c * 4 + k] = ((a[0 * 4 + k] * b[c * 4 + 0] + a[1 * 4 + k] * b[c * 4 + 1]) + a[2 * 4 + k] * b[c * 4 + 2]) + a[3 * 4 + k] * b[c * 4 + 3];
+    memcpy(r, t, sizeof(t));
+}
+
+// Frustum planes of CullMeshlets — Shading.cpp:779-792. planes[i] for i<5 are the ones tested (:806).
+void orc_frustum_planes(const float* proj, const float* view, const float* model, float* planes /*[6][4]*/) {
+    float pv[16], pvm[16];
+    mat4_mul(proj, view, pv);
+    mat4_mul(pv, model, pvm);
+    // transpose: row i of pvm = (pvm[0*4+i], pvm[1*4+i], pvm[2*4+i], pvm[3*4+i])
+    for (int i = 0; i < 3; i++) {
+        float a[4], b[4];
+        for (int c = 0; c < 4; c++) {
+            a[c] = pvm[c * 4 + 3] + pvm[c * 4 + i];
+            b[c] = pvm[c * 4 + 3] - pvm[c * 4 + i];
+        }
+        float la = std::sqrt((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);   // glm::length = sqrt(dot)
+        float lb = std::sqrt((b[0] * b[0] + b[1] * b[1]) + b[2] * b[2]);
+        for (int c = 0; c < 4; c++) {
+            planes[(i * 2 + 0) * 4 + c] = a[c] / la;
+            planes[(i * 2 + 1) * 4 + c] = b[c] / lb;
+        }
+    }
+}
+
+// CullMeshlets, frustum part — Shading.cpp:795-809, :865-867. Returns the visible count.
+uint32_t orc_cull_meshlets(uint16_t* bitmap, const swr_meshlet* meshlets, uint32_t count, const float* planes /*[5][4]*/) {
+    uint32_t visibleCount = 0;
+    for (uint32_t offset = 0; offset < count; offset += 16) {
+        uint16_t bits = 0;
+        for (uint32_t l = 0; l < 16 && offset + l < count; l++) {
+            const swr_meshlet& m = meshlets[offset + l];
+            bool visible = true;
+            for (int i = 0; i < 5; i++) {
+                const float* p = planes + i * 4;
+                // simd::dot(v3,v3) = fma(a.x,b.x, fma(a.y,b.y, a.z*b.z)) — SIMD.h:437
+                float dist = std::fmaf(m.BoundCenter[0], p[0], std::fmaf(m.BoundCenter[1], p[1], m.BoundCenter[2] * p[2])) + p[3];
+                visible = visible && (dist > -m.BoundRadius);
+            }
+            if (visible) { bits |= (uint16_t)(1u << l); visibleCount++; }
+        }
+        bitmap[offset / 16] = bits;
+    }
+    return visibleCount;
+}
+
+const char* orc_build_info() {
+    return "oracle: scalar canonical restatement; parity unpinned (reference has no golden vectors)"
+#if defined(__FMA__)
+           "; hw-fma"
+#endif
+        ;
+}
+
+}  // extern "C"

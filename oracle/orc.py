@@ -1,0 +1,100 @@
+"""ctypes binding of oracle/liboracle.so (test infrastructure; see oracle.cpp header)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    path = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".cpp")]
+    stale = (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return path
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_build_info.restype = C.c_char_p
+        _LIB.orc_cull_meshlets.restype = C.c_uint32
+    return _LIB
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _mat(m) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(m, dtype=np.float32).reshape(16))
+
+
+class Framebuffer:
+    """Host mirror of swr::Framebuffer (Rasterizer.h:10-78): [layers, LayerStride] u32, 4x4-tiled."""
+
+    def __init__(self, width: int, height: int, layers: int = 2):
+        assert width % 4 == 0 and height % 4 == 0
+        self.width, self.height, self.layers = width, height, layers
+        self.layer_stride = (width * height + 63) & ~63
+        self.data = np.zeros((layers, self.layer_stride), dtype=np.uint32)
+
+    def clear(self, color: int, depth: float):
+        self.data[0, :] = np.uint32(color)
+        self.data[1, :] = np.float32(depth).view(np.uint32)
+
+    def get_pixels(self, layer: int) -> np.ndarray:
+        out = np.zeros((self.height, self.width), dtype=np.uint32)
+        lib().orc_fb_get_pixels(_p(self.data[layer]), self.width, self.height, _p(out), self.width)
+        return out
+
+
+def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, count: int, object_to_clip,
+                  cull_bitmap=None, materials=None, guardband: bool = True, counters=None) -> np.ndarray:
+    """Rasterizer::DrawMeshlets + VisBufferShader on the CPU. Returns the 4 integer perf counters."""
+    if counters is None:
+        counters = np.zeros(4, dtype=np.uint64)
+    m = _mat(object_to_clip)
+    cb = None if cull_bitmap is None else _p(np.ascontiguousarray(cull_bitmap, dtype=np.uint16))
+    mats = None if materials is None or len(materials) == 0 else _p(materials)
+    lib().orc_draw_meshlets(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
+                            C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats,
+                            C.c_uint32(1 if guardband else 0), _p(counters))
+    return counters
+
+
+def frustum_planes(proj, view, model) -> np.ndarray:
+    out = np.zeros((6, 4), dtype=np.float32)
+    lib().orc_frustum_planes(_p(_mat(proj)), _p(_mat(view)), _p(_mat(model)), _p(out))
+    return out
+
+
+def cull_meshlets(meshlets: np.ndarray, planes: np.ndarray):
+    bitmap = np.zeros((len(meshlets) + 15) // 16, dtype=np.uint16)
+    pl = np.ascontiguousarray(planes[:5], dtype=np.float32)
+    n = lib().orc_cull_meshlets(_p(bitmap), _p(meshlets), C.c_uint32(len(meshlets)), _p(pl))
+    return bitmap, int(n)
+
+
+def probe_triangle(verts, width: int, height: int, cull_mode: int = 1, guardband: bool = True):
+    """One triangle through classify + early setup + bbox + late setup (known-answer probes)."""
+    v = np.ascontiguousarray(np.asarray(verts, dtype=np.float32).reshape(12))
+    cc = C.c_int(0)
+    pos = np.zeros(3, dtype=np.uint32)
+    bbox = np.zeros(2, dtype=np.uint32)
+    edges = np.zeros(9, dtype=np.int32)
+    zw = np.zeros(7, dtype=np.float32)
+    keep = lib().orc_probe_triangle(_p(v), width, height, cull_mode, 1 if guardband else 0, C.byref(cc),
+                                    _p(pos), _p(bbox), _p(edges), _p(zw))
+    return dict(keep=int(keep), cc=cc.value, pos=pos, bbox=bbox, edges=edges, zw=zw)
