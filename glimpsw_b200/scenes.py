@@ -91,6 +91,17 @@ class SceneData:
         return cam.object_to_clip(p, v, node.model)
 
 
+def concat_meshlets(parts) -> np.ndarray:
+    """np.concatenate re-packs padded structured dtypes (1728 -> 1723 bytes); copy into a fresh array instead."""
+    out = np.zeros(sum(len(p) for p in parts), dtype=MESHLET_DTYPE)
+    k = 0
+    for p in parts:
+        assert p.dtype == MESHLET_DTYPE
+        out[k:k + len(p)] = p
+        k += len(p)
+    return out
+
+
 def set_bounds(meshlets: np.ndarray) -> None:
     """Bounding sphere per meshlet (Scene.cpp:239-241 stores meshopt's; here: bbox centre + max distance)."""
     nv = meshlets["NumVertices"].astype(np.int64)
@@ -301,3 +312,100 @@ def orbit_cameras(scene: SceneData, count: int, seed: int = 5, radius: float = 6
         pos = (math.sin(ang) * rad, (r[i, 2] - 0.5) * 3.0, math.cos(ang) * rad)
         cams.append(cam.Camera(position=pos, euler=(-ang, -0.1), fov_deg=90.0, aspect=scene.width / scene.height))
     return cams
+
+
+# ---------------------------------------------------------------------------------------------
+def default_light() -> np.ndarray:
+    """The directional light Playground installs when a scene has none (Main.cpp:192-201)."""
+    l = np.zeros(1, dtype=LIGHT_DTYPE)
+    d = -np.array([0.589494, 0.684509, 0.428906])
+    l["Type"] = 0
+    l["Direction"] = (d / np.linalg.norm(d)).astype(f32)
+    l["Color"] = (1.0, 1.0, 1.0)
+    l["Intensity"] = 1500.0
+    return l
+
+
+def make_light(kind: int, position=(0, 0, 0), direction=(0, -1, 0), color=(1, 1, 1), intensity=1500.0, radius=0.0,
+               inner=0.3, outer=0.6) -> np.ndarray:
+    """Light with the pre-computed fields of Light::SetRadius / SetSpotAngles (Scene.h:66-75)."""
+    l = np.zeros(1, dtype=LIGHT_DTYPE)
+    d = np.asarray(direction, dtype=np.float64)
+    l["Type"], l["Position"], l["Direction"] = kind, position, (d / np.linalg.norm(d)).astype(f32)
+    l["Color"], l["Intensity"] = color, intensity
+    rad = radius if radius > 0 else 1e6
+    l["Radius"] = rad
+    l["InvRadiusSq"] = f32(1.0) / (f32(rad) * f32(rad))
+    l["SpotInnerAngle"], l["SpotOuterAngle"] = inner, outer
+    sc = f32(1.0) / max(f32(math.cos(inner)) - f32(math.cos(outer)), f32(1e-4))
+    l["SpotScale"] = sc
+    l["SpotOffset"] = -f32(math.cos(outer)) * sc
+    return l
+
+
+def torus_knot_scene(nu: int = 300, nv: int = 120, width: int = 1920, height: int = 1080, tex_size: int = 1024,
+                     seed: int = 11, extra_lights: bool = False, alpha_material: bool = False) -> SceneData:
+    """BASELINE config C1 stand-in (DamagedHelmet is not among the assets): a (2,3) torus knot of
+    2*nu*nv triangles (72,000 by default) with UVs, normals and tangents, split over two materials that
+    each bind a two-layer 1024^2 texture, lit by the default directional light."""
+    from . import textures as tx
+
+    u = np.linspace(0, 2 * math.pi, nu, endpoint=False)
+    v = np.linspace(0, 2 * math.pi, nv, endpoint=False)
+    p, q, R, r0, tube = 2, 3, 2.0, 0.8, 0.42
+    cu = np.stack([(R + r0 * np.cos(q * u)) * np.cos(p * u), r0 * np.sin(q * u), (R + r0 * np.cos(q * u)) * np.sin(p * u)], 1)
+    du = np.roll(cu, -1, 0) - np.roll(cu, 1, 0)
+    T = du / np.linalg.norm(du, axis=1, keepdims=True)
+    up = np.array([0.0, 1.0, 0.0])
+    Nn = np.cross(T, up); Nn /= np.linalg.norm(Nn, axis=1, keepdims=True)
+    B = np.cross(T, Nn)
+    cv, sv = np.cos(v), np.sin(v)
+    normal = Nn[:, None, :] * cv[None, :, None] + B[:, None, :] * sv[None, :, None]           # [nu, nv, 3]
+    pos = cu[:, None, :] + tube * normal
+    tang = np.broadcast_to(T[:, None, :], normal.shape)
+    uvs = np.stack(np.broadcast_arrays((np.arange(nu) / nu * 2.0)[:, None], (np.arange(nv) / nv)[None, :]), -1)
+    # closed surface: the UV seam needs duplicated vertices; add one extra ring/column
+    def wrap(a):
+        a = np.concatenate([a, a[:1]], 0)
+        return np.concatenate([a, a[:, :1]], 1)
+    pos, normal, tang = wrap(pos), wrap(normal), wrap(tang)
+    uvs = wrap(uvs)
+    uvs[-1, :, 0] = 2.0
+    uvs[:, -1, 1] = 1.0
+    rows, cols = nu + 1, nv + 1
+    ii, jj = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    v00, v01, v10, v11 = ii * cols + jj, ii * cols + jj + 1, (ii + 1) * cols + jj, (ii + 1) * cols + jj + 1
+    tris = np.stack([np.stack([v00, v10, v01], -1), np.stack([v01, v10, v11], -1)], 2).reshape(-1, 3)
+    P, Nf, Tf, UV = pos.reshape(-1, 3), normal.reshape(-1, 3), tang.reshape(-1, 3), uvs.reshape(-1, 2)
+    Tf4 = np.concatenate([Tf, np.where((np.arange(len(Tf)) % 7) == 0, -1.0, 1.0)[:, None]], 1)
+
+    half = len(tris) // 2
+    materials = np.zeros(2, dtype=MATERIAL_DTYPE)
+    materials["TextureId"] = [0, 1]
+    materials["AlphaCutoff"] = [255, 128 if alpha_material else 255]
+    materials["IsDoubleSided"] = [0, 1 if alpha_material else 0]
+    # triangle winding: front faces must have det > 0 in this renderer's screen space
+    m0 = meshletize(P, tris[:half][:, [0, 2, 1]], uv=UV, normals=Nf, tangents=Tf4, material_id=0, alpha_cutoff=255)
+    m1 = meshletize(P, tris[half:][:, [0, 2, 1]], uv=UV, normals=Nf, tangents=Tf4, material_id=1,
+                    alpha_cutoff=128 if alpha_material else 255)
+    meshlets = concat_meshlets([m0, m1])
+    texs =[tx.procedural_material_texture(tex_size, seed), tx.procedural_material_texture(tex_size, seed + 1, alpha_holes=alpha_material)]
+    lights = default_light()
+    if extra_lights:
+        lights = np.concatenate([lights, make_light(1, position=(0.5, 2.0, 3.0), color=(1.0, 0.6, 0.3), intensity=4000.0, radius=12.0),
+                                 make_light(2, position=(-3.0, 3.0, 2.0), direction=(0.6, -0.7, -0.4), color=(0.3, 0.6, 1.0),
+                                            intensity=9000.0, radius=20.0, inner=0.25, outer=0.55)])
+    model = cam.mat_mul(cam.translate((0.0, 0.2, 0.0)), cam.mat_mul(cam.rotate_axis((0.3, 1.0, 0.1), 0.6), cam.scale(0.9)))
+    camera = cam.Camera(position=(0.2, 1.0, 3.2), euler=(0.05, -0.28), fov_deg=90.0, aspect=width / height)
+    return SceneData(f"torusknot{nu}x{nv}", meshlets, [DrawNode(0, len(meshlets), model)], camera, width, height,
+                     materials=materials, textures=texs, lights=lights)
+
+
+def resolve_uniforms(scene: SceneData, node: DrawNode, exposure: float = 1.0) -> dict:
+    """The ShadingContext fields Resolve reads (Shading.h:21-33, Shading.cpp:659)."""
+    proj, view = scene.view_proj()
+    w2c = cam.mat_mul(proj, view)
+    return dict(world_to_clip=w2c, object_to_clip=cam.mat_mul(w2c, node.model),
+                object_to_world3=np.ascontiguousarray(node.model[0:3, 0:3]),
+                inv_screen_proj=cam.inverse_screen_proj(w2c, scene.width, scene.height),
+                view_pos=scene.camera.position.astype(f32), exposure=exposure)

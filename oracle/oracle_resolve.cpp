@@ -1,0 +1,454 @@
+// oracle_resolve.cpp — CPU restatement of the vis-buffer resolve pass (ShadingContext::Resolve).
+//
+// TEST INFRASTRUCTURE ONLY (see oracle.cpp header). PARITY UNPINNED: the reference has no golden
+// images. Follows, per 4x4 fragment with 16 lanes like the reference:
+//   ShadingContext::Resolve            Shading.cpp:658-689   (+ DispatchPass Rasterizer.h:225-242)
+//   ResolveSurface / IntersectTriangle Shading.cpp:472-579 / :417-464
+//   EvalLighting / GetLightAttenuation Shading.cpp:602-645 / :581-600, BRDF helpers :17-33
+//   Texture2D::SampleLevel/SampleLinear Texture.h:412-459, :506-575; CalcMipLevel :276-280
+//   pixfmt::RGBA8u::{Unpack,UnpackSrgb,Pack} Texture.h:28-67; RG16f::Unpack :109-124
+//   texutil::UnmapOctahedron           Texture.h:289-296
+// Canonical arithmetic: approx_rcp -> 1/x, approx_rsqrt -> 1/sqrt(x) (the AVX-512 14-bit tables are
+// not reproducible elsewhere; the colour gate is a tolerance: max abs error <= 2/255, PSNR >= 50 dB).
+// Two reference behaviours that read uninitialised lanes are pinned:
+//   * the nearest-vs-bilinear choice `any(mipLevel > 0)` spans the NON-SKY lanes of the tile;
+//   * sky lanes (depth <= 0) always resolve to colour 0 (there is no skybox on this path).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "../include/swr_types.h"
+
+namespace {
+
+constexpr int N = 16;
+constexpr float kInvPi = 0.3183098861837907f;   // SIMD.h:386
+
+inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline int32_t round2i(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)std::nearbyintf(x);
+}
+inline float approx_rcp(float x) { return 1.0f / x; }
+inline float approx_rsqrt(float x) { return 1.0f / std::sqrt(x); }
+inline float approx_sqrt(float x) { return approx_rsqrt(x) * x; }        // SIMD.h:296
+inline float lerpf(float a, float b, float t) { return std::fmaf(t, b, std::fmaf(-t, a, a)); }   // SIMD.h:445
+inline float clampf(float x, float a, float b) { return std::fmin(std::fmax(x, a), b); }
+inline float mulsign(float x, float y) { return u2f(f2u(x) ^ (f2u(y) & 0x80000000u)); }          // SIMD.h:341-344
+inline int32_t ilog2(float x) { return ((int32_t)f2u(x) - (127 << 23)) >> 23; }                  // SIMD.h:426
+
+struct V3 { float x, y, z; };
+inline float dot3(V3 a, V3 b) { return std::fmaf(a.x, b.x, std::fmaf(a.y, b.y, a.z * b.z)); }   // SIMD.h:437
+inline V3 normalize3(V3 a) { float r = approx_rsqrt(dot3(a, a)); return { a.x * r, a.y * r, a.z * r }; }   // SIMD.h:443
+inline V3 cross3(V3 a, V3 b) {                                                                    // SIMD.h:435-441
+    return { std::fmaf(a.y, b.z, -a.z * b.y), std::fmaf(a.z, b.x, -a.x * b.z), std::fmaf(a.x, b.y, -a.y * b.x) };
+}
+inline V3 mul_mat3(const float* m, V3 n) {                                                        // SIMD.h:465-471
+    return { std::fmaf(n.x, m[0], std::fmaf(n.y, m[3], n.z * m[6])),
+             std::fmaf(n.x, m[1], std::fmaf(n.y, m[4], n.z * m[7])),
+             std::fmaf(n.x, m[2], std::fmaf(n.y, m[5], n.z * m[8])) };
+}
+inline void mul_mat4(const float* m, float x, float y, float z, float w, float out[4]) {          // SIMD.h:457-464
+    for (int r = 0; r < 4; r++)
+        out[r] = std::fmaf(x, m[0 * 4 + r], std::fmaf(y, m[1 * 4 + r], std::fmaf(z, m[2 * 4 + r], w * m[3 * 4 + r])));
+}
+inline float bary_lerp(const float b[3], float v0, float v1, float v2) {                          // Rasterizer.h:101-104
+    return std::fmaf(v0, b[0], std::fmaf(v1, b[1], v2 * b[2]));
+}
+
+inline float half2float(uint16_t h) {   // _mm512_cvtph_ps (exact)
+    uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 31, man = h & 1023;
+    if (exp == 0) {
+        if (man == 0) return u2f(sign);
+        float f = (float)man * (1.0f / 16777216.0f);   // man * 2^-24
+        return u2f(f2u(f) | sign);
+    }
+    if (exp == 31) return u2f(sign | 0x7F800000u | (man << 13));
+    return u2f(sign | ((exp + 112) << 23) | (man << 13));
+}
+
+// texutil::UnmapOctahedron — Texture.h:289-296
+inline V3 unmap_octahedron(float u, float v) {
+    u = u * 2.0f - 1.0f; v = v * 2.0f - 1.0f;
+    V3 n = { u, v, 1.0f - std::fabs(u) - std::fabs(v) };
+    float t = std::fmax(-n.z, 0.0f);
+    n.x -= mulsign(t, n.x);
+    n.y -= mulsign(t, n.y);
+    return normalize3(n);
+}
+// UnpackNormalTangent — Shading.cpp:232-236 (RGBA8u::Unpack, Texture.h:28-36)
+inline void unpack_normal_tangent(uint32_t p, V3& n, V3& t) {
+    const float s = 1.0f / 255;
+    float a = (float)(p & 255) * s, b = (float)((p >> 8) & 255) * s, c = (float)((p >> 16) & 255) * s, d = (float)((p >> 24) & 255) * s;
+    n = unmap_octahedron(a, b);
+    t = unmap_octahedron(c, d);
+}
+
+// ---- texture sampling -----------------------------------------------------------------------
+inline uint32_t texel_offset(uint32_t x, uint32_t y, uint32_t stride) {        // Texture.h:494-501 (TiledY8)
+    return (y & 7u) | (x << 3) | ((y & ~7u) << stride);
+}
+inline uint32_t lerp16(uint32_t a, uint32_t b, uint32_t t) {                    // SIMD.h:448-450 on both s16 halves
+    uint32_t r = 0;
+    for (int h = 0; h < 2; h++) {
+        int16_t ah = (int16_t)(a >> (16 * h)), bh = (int16_t)(b >> (16 * h)), th = (int16_t)(t >> (16 * h));
+        int16_t diff = (int16_t)(bh - ah);
+        int16_t m = (int16_t)((((int32_t)diff * (int32_t)th) + (1 << 14)) >> 15);   // vpmulhrsw
+        r |= (uint32_t)(uint16_t)(int16_t)(ah + m) << (16 * h);
+    }
+    return r;
+}
+// CalcMipLevel(grad, scale) — Texture.h:276-280
+inline int32_t calc_mip_level(const float g[4], float scaleU, float scaleV) {
+    float dx = std::fmaf(g[0], g[0], g[1] * g[1]) * (scaleU * scaleU);
+    float dy = std::fmaf(g[2], g[2], g[3] * g[3]) * (scaleV * scaleV);
+    return ilog2(std::fmax(dx, dy)) >> 1;
+}
+// Texture2D::SampleLevel<Repeat, mag Linear, min Nearest> for one lane — Texture.h:412-459, :506-575.
+// `useNearest` is the tile-wide filter decision (`simd::any(mipLevel > 0)`, :432).
+inline uint32_t sample_level(const swr_texture_desc& t, float u, float v, uint32_t layer, int32_t mipLevel, bool useNearest) {
+    const int32_t maskLerpU = (int32_t)(t.Width << 8) - 1, maskLerpV = (int32_t)(t.Height << 8) - 1;   // :627-628
+    const float scaleLerpU = (float)(maskLerpU + 1), scaleLerpV = (float)(maskLerpV + 1);
+    float su = u * scaleLerpU, sv = v * scaleLerpV;
+    int32_t ix = round2i(su) & maskLerpU, iy = round2i(sv) & maskLerpV;       // Repeat (:424-426)
+    int32_t maxLevel = (int32_t)t.MipLevels - 1;
+    mipLevel = mipLevel < 0 ? 0 : (mipLevel > maxLevel ? maxLevel : mipLevel);
+    uint32_t offset = layer * t.LayerStride;
+    uint32_t stride = t.RowShift;
+    if (mipLevel > 0) {                                                       // :443-447 (no-op for level 0)
+        ix >>= mipLevel; iy >>= mipLevel;
+        stride -= (uint32_t)mipLevel;
+        offset += t.MipOffsets[mipLevel];
+    }
+    if (useNearest) return t.Data[offset + texel_offset((uint32_t)(ix >> 8), (uint32_t)(iy >> 8), stride)];   // :450-451
+
+    // SampleLinear (:506-575)
+    int32_t ixf = ix - 127 > 0 ? ix - 127 : 0, iyf = iy - 127 > 0 ? iy - 127 : 0;
+    int32_t tx = ixf >> 8, ty = iyf >> 8;
+    bool inboundX = ((tx + 1) << mipLevel) < (int32_t)t.Width;
+    bool inboundY = ((ty + 1) << mipLevel) < (int32_t)t.Height;
+    uint32_t i00 = offset + texel_offset((uint32_t)tx, (uint32_t)ty, stride);
+    uint32_t d00 = t.Data[i00], d10 = t.Data[i00 + 8];
+    uint32_t i01 = offset + texel_offset((uint32_t)tx, (uint32_t)(ty + (inboundY ? 1 : 0)), stride);
+    uint32_t d01 = t.Data[i01], d11 = t.Data[i01 + 8];
+    uint32_t fx = (uint32_t)(ixf & 255) << 7, fy = (uint32_t)(iyf & 255) << 7;
+    fx = (fx << 16) | fx; fy = (fy << 16) | fy;
+    if (!inboundX) fx = 0;
+    uint32_t rbRow1 = lerp16(d00 & 0x00FF00FFu, d10 & 0x00FF00FFu, fx);
+    uint32_t gaRow1 = lerp16((d00 >> 8) & 0x00FF00FFu, (d10 >> 8) & 0x00FF00FFu, fx);
+    uint32_t rbRow2 = lerp16(d01 & 0x00FF00FFu, d11 & 0x00FF00FFu, fx);
+    uint32_t gaRow2 = lerp16((d01 >> 8) & 0x00FF00FFu, (d11 >> 8) & 0x00FF00FFu, fx);
+    uint32_t rbCol = lerp16(rbRow1, rbRow2, fy);
+    uint32_t gaCol = lerp16(gaRow1, gaRow2, fy);
+    return rbCol | (gaCol << 8);
+}
+
+// RGBA8u::UnpackSrgb — Texture.h:37-54
+inline void unpack_srgb(uint32_t packed, float out[4]) {
+    uint32_t rb1 = ((packed << 8) & 0xFF00FF00u) + 0x00FF00FFu;
+    uint32_t ag1 = (packed & 0xFF00FF00u) + 0x00FF00FFu;
+    auto mulhi16 = [](uint32_t a) {
+        uint32_t lo = a & 0xFFFF, hi = a >> 16;
+        return ((lo * lo) >> 16) | (((hi * hi) >> 16) << 16);
+    };
+    uint32_t rb2 = mulhi16(rb1), ag2 = mulhi16(ag1);
+    const float scale = 1.0f / 65535;
+    out[0] = (float)(rb2 & 65535) * scale;
+    out[1] = (float)(ag2 & 65535) * scale;
+    out[2] = (float)(rb2 >> 16) * scale;
+    out[3] = (float)(ag1 >> 16) * scale;
+}
+// RGBA8u::Pack — Texture.h:55-67 (vcvtps2dq RNE, packssdw, packuswb saturation)
+inline uint32_t pack_rgba8(float r, float g, float b, float a) {
+    auto ch = [](float v) -> uint32_t {
+        int32_t i = round2i(v * 255.0f);
+        i = i < -32768 ? -32768 : (i > 32767 ? 32767 : i);
+        i = i < 0 ? 0 : (i > 255 ? 255 : i);
+        return (uint32_t)i;
+    };
+    return ch(r) | (ch(g) << 8) | (ch(b) << 16) | (ch(a) << 24);
+}
+
+// BRDF helpers — Shading.cpp:17-33
+inline float pow5(float x) { return (x * x) * (x * x) * x; }
+inline float D_GGX(float NoH, float roughness) {
+    float a = NoH * roughness;
+    float k = roughness * approx_rcp(1.0f - NoH * NoH + a * a);
+    return k * k * kInvPi;
+}
+inline float V_SmithGGXCorrelatedFast(float NoV, float NoL, float roughness) {
+    float a = 2.0f * NoL * NoV;
+    float b = NoL + NoV;
+    return 0.5f / lerpf(a, b, roughness);
+}
+inline float F_Schlick1(float u, float f0) {
+    float f = pow5(1.0f - u);
+    return f + f0 * (1.0f - f);
+}
+
+// GetLightAttenuation — Shading.cpp:581-600
+inline float light_attenuation(const swr_light& light, V3 p) {
+    if (light.Type == 0) return 1.0f;
+    V3 posToLight = { light.Position[0] - p.x, light.Position[1] - p.y, light.Position[2] - p.z };
+    float distanceSquare = dot3(posToLight, posToLight);
+    float factor = distanceSquare * light.InvRadiusSq;
+    float smoothFactor = std::fmax(1.0f - factor * factor, 0.0f);
+    float attenuation = (smoothFactor * smoothFactor) * approx_rcp(std::fmax(distanceSquare, 1e-4f));
+    if (light.Type == 2) {
+        V3 nl = normalize3(posToLight);
+        V3 nd = { -light.Direction[0], -light.Direction[1], -light.Direction[2] };
+        float cd = dot3(nd, nl);
+        float spot = clampf(cd * light.SpotScale + light.SpotOffset, 0.0f, 1.0f);
+        attenuation *= spot * spot;
+    }
+    return attenuation;
+}
+
+struct Surface { uint32_t albedo; V3 normal; float metallic, roughness; };
+
+}  // namespace
+
+extern "C" {
+
+// ShadingContext::Resolve over the whole framebuffer. color/depth are the 4x4-tiled layers 0/1;
+// layer 0 holds surface ids on entry and RGBA8 colour on exit (Shading.cpp:688).
+void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                 const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                 const swr_light* lights, uint32_t numLights,
+                 const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                 const float* viewPos, float exposure) {
+    const float scaleU = 2.0f / (float)width, scaleV = 2.0f / (float)height;       // Rasterizer.h:226
+    const float centerU = 0.5f * scaleU - 1.0f, centerV = 0.5f * scaleV - 1.0f;    // :227
+    const V3 view = { viewPos[0], viewPos[1], viewPos[2] };
+    const float lightExposure = exposure * 0.001f;                                  // Shading.cpp:674
+
+    for (uint32_t y0 = 0; y0 < height; y0 += 4) {
+        for (uint32_t x0 = 0; x0 < width; x0 += 4) {
+            uint32_t tileOffset = ((x0 & ~3u) << 2) + (y0 & ~3u) * width;           // Rasterizer.h:50-56
+            const float* tileDepth = depth + tileOffset;
+            uint32_t* tileData = color + tileOffset;
+            bool sky[N];
+            bool anySurface = false;
+            V3 worldPos[N];
+            float screenU[N], screenV[N];
+            for (int i = 0; i < N; i++) {
+                sky[i] = tileDepth[i] <= 0.0f;                                      // :664
+                anySurface = anySurface || !sky[i];
+                float px = (float)(int32_t)(x0 + (i & 3)), py = (float)(int32_t)(y0 + (i >> 2));
+                screenU[i] = px * scaleU + centerU;                                 // Rasterizer.h:237
+                screenV[i] = py * scaleV + centerV;
+                float h[4];
+                mul_mat4(invScreenProj, px, py, sky[i] ? 1.0f : tileDepth[i], 1.0f, h);   // :666-667
+                float rw = 1.0f / h[3];
+                worldPos[i] = { h[0] * rw, h[1] * rw, h[2] * rw };
+            }
+            float outColor[N][3];
+            for (int i = 0; i < N; i++) outColor[i][0] = outColor[i][1] = outColor[i][2] = 0.0f;
+
+            if (anySurface) {
+                // ---- ResolveSurface (Shading.cpp:472-579)
+                float bary[N][3], ddx[N][3], ddy[N][3];
+                uint32_t packedTC[N][3], packedNT[N][3], handed[N], materialId[N];
+                float texU[N], texV[N], texGrad[N][4];
+                for (int i = 0; i < N; i++) {
+                    if (sky[i]) continue;
+                    uint32_t sid = tileData[i];
+                    const swr_meshlet& mesh = meshlets[sid / SWR_MAX_PRIMS];
+                    uint32_t tri = sid % SWR_MAX_PRIMS;
+                    float clip[3][4];
+                    handed[i] = 0;
+                    for (int vi = 0; vi < 3; vi++) {
+                        uint32_t idx = mesh.Indices[vi][tri];
+                        mul_mat4(objectToClip, mesh.Positions[0][idx & 63], mesh.Positions[1][idx & 63], mesh.Positions[2][idx & 63], 1.0f, clip[vi]);   // :509-511
+                        packedTC[i][vi] = mesh.TexCoords[idx & 63];
+                        packedNT[i][vi] = mesh.NormalTangents[idx & 63];
+                        if (vi == 0 && ((mesh.TangentHandedness >> (idx & 63)) & 1)) handed[i] = 1u << 31;   // :500-502
+                    }
+                    materialId[i] = mesh.MaterialId;
+
+                    // IntersectTriangle (Shading.cpp:417-464)
+                    float invW[3] = { 1.0f / clip[0][3], 1.0f / clip[1][3], 1.0f / clip[2][3] };
+                    float p0x = clip[0][0] * invW[0], p0y = clip[0][1] * invW[0];
+                    float p1x = clip[1][0] * invW[1], p1y = clip[1][1] * invW[1];
+                    float p2x = clip[2][0] * invW[2], p2y = clip[2][1] * invW[2];
+                    float m0x = p2x - p1x, m0y = p2y - p1y, m1x = p0x - p1x, m1y = p0y - p1y;
+                    float invDet = 1.0f / (m0x * m1y - m1x * m0y);
+                    float sx[3], sy[3], dsum = 0, esum = 0;
+                    float dxv[3] = { p1y - p2y, p2y - p0y, p0y - p1y }, dyv[3] = { p2x - p1x, p0x - p2x, p1x - p0x };
+                    for (int k = 0; k < 3; k++) { sx[k] = dxv[k] * (invDet * invW[k]); sy[k] = dyv[k] * (invDet * invW[k]); }
+                    dsum = sx[0] + sx[1] + sx[2];
+                    esum = sy[0] + sy[1] + sy[2];
+                    float rel0x = screenU[i] - p0x, rel0y = screenV[i] - p0y;
+                    float interpInvW = invW[0] + rel0x * dsum + rel0y * esum;
+                    float interpW = 1.0f / interpInvW;
+                    bary[i][1] = interpW * (rel0x * sx[1] + rel0y * sy[1]);
+                    bary[i][2] = interpW * (rel0x * sx[2] + rel0y * sy[2]);
+                    bary[i][0] = 1 - bary[i][1] - bary[i][2];
+                    float kx = 2.0f / (float)width, ky = -(2.0f / (float)height);   // :454-457
+                    for (int k = 0; k < 3; k++) { sx[k] *= kx; sy[k] *= ky; }
+                    dsum *= kx; esum *= ky;
+                    float interpW_ddx = 1.0f / (interpInvW + dsum), interpW_ddy = 1.0f / (interpInvW + esum);
+                    for (int k = 0; k < 3; k++) {
+                        ddx[i][k] = interpW_ddx * (bary[i][k] * interpInvW + sx[k]) - bary[i][k];
+                        ddy[i][k] = interpW_ddy * (bary[i][k] * interpInvW + sy[k]) - bary[i][k];
+                    }
+
+                    // UVs and UV gradients (:516-527); RG16f::Unpack (Texture.h:109-124)
+                    float t0u = half2float((uint16_t)packedTC[i][0]), t0v = half2float((uint16_t)(packedTC[i][0] >> 16));
+                    float t10u = half2float((uint16_t)packedTC[i][1]) - t0u, t10v = half2float((uint16_t)(packedTC[i][1] >> 16)) - t0v;
+                    float t20u = half2float((uint16_t)packedTC[i][2]) - t0u, t20v = half2float((uint16_t)(packedTC[i][2] >> 16)) - t0v;
+                    texU[i] = t0u + t10u * bary[i][1] + t20u * bary[i][2];
+                    texV[i] = t0v + t10v * bary[i][1] + t20v * bary[i][2];
+                    texGrad[i][0] = t10u * ddx[i][1] + t20u * ddx[i][2];
+                    texGrad[i][1] = t10v * ddx[i][1] + t20v * ddx[i][2];
+                    texGrad[i][2] = t10u * ddy[i][1] + t20u * ddy[i][2];
+                    texGrad[i][3] = t10v * ddy[i][1] + t20v * ddy[i][2];
+                }
+
+                // material waterfall (:532-545)
+                uint32_t packedAlbedo[N] = {}, packedNMR[N] = {};
+                bool done[N];
+                for (int i = 0; i < N; i++) done[i] = sky[i] || materialId[i] == SWR_NO_MATERIAL;
+                for (int i = 0; i < N; i++) {
+                    if (done[i]) continue;
+                    uint32_t id = materialId[i];
+                    const swr_texture_desc& tex = textures[materials[id].TextureId];
+                    int32_t mip[N];
+                    bool anyMin = false;
+                    for (int l = 0; l < N; l++) {
+                        if (sky[l]) continue;                                  // pinned: see header
+                        mip[l] = calc_mip_level(texGrad[l], (float)tex.Width, (float)tex.Height);
+                        anyMin = anyMin || mip[l] > 0;                         // Texture.h:432
+                    }
+                    for (int l = 0; l < N; l++) {
+                        if (sky[l] || materialId[l] != id) continue;
+                        packedAlbedo[l] = sample_level(tex, texU[l], texV[l], 0, mip[l], anyMin);
+                        if (tex.NumLayers >= 2) packedNMR[l] = sample_level(tex, texU[l], texV[l], 1, mip[l], anyMin);
+                        done[l] = true;
+                    }
+                }
+
+                bool anyNormalMap = false;
+                for (int i = 0; i < N; i++) anyNormalMap = anyNormalMap || (!sky[i] && (packedNMR[i] & 0xFFFF) != 0);   // :554
+
+                Surface surf[N];
+                for (int i = 0; i < N; i++) {
+                    if (sky[i]) continue;
+                    V3 n0, n1, n2, t0, t1, t2;
+                    unpack_normal_tangent(packedNT[i][0], n0, t0);
+                    unpack_normal_tangent(packedNT[i][1], n1, t1);
+                    unpack_normal_tangent(packedNT[i][2], n2, t2);
+                    V3 nl = { bary_lerp(bary[i], n0.x, n1.x, n2.x), bary_lerp(bary[i], n0.y, n1.y, n2.y), bary_lerp(bary[i], n0.z, n1.z, n2.z) };
+                    V3 normalWS = normalize3(mul_mat3(objectToWorld3, nl));
+                    V3 normal = normalWS;
+                    if (anyNormalMap) {
+                        V3 tl = { bary_lerp(bary[i], t0.x, t1.x, t2.x), bary_lerp(bary[i], t0.y, t1.y, t2.y), bary_lerp(bary[i], t0.z, t1.z, t2.z) };
+                        V3 tangentWS = normalize3(mul_mat3(objectToWorld3, tl));
+                        V3 bit = cross3(normalWS, tangentWS);
+                        bit = { u2f(f2u(bit.x) ^ handed[i]), u2f(f2u(bit.y) ^ handed[i]), u2f(f2u(bit.z) ^ handed[i]) };
+                        float nx = (float)(packedNMR[i] & 255) * (1.0f / 127.5f) - 1.0f;
+                        float ny = (float)((packedNMR[i] >> 8) & 255) * (1.0f / 127.5f) - 1.0f;
+                        float nz = approx_sqrt(1.0f - (nx * nx + ny * ny));
+                        normal = normalize3({ nx * tangentWS.x + ny * bit.x + nz * normalWS.x,
+                                              nx * tangentWS.y + ny * bit.y + nz * normalWS.y,
+                                              nx * tangentWS.z + ny * bit.z + nz * normalWS.z });
+                    }
+                    surf[i] = { packedAlbedo[i], normal, (float)((packedNMR[i] >> 16) & 255) * (1.0f / 255),
+                                (float)((packedNMR[i] >> 24) & 255) * (1.0f / 255) };
+                }
+
+                // ---- EvalLighting (Shading.cpp:602-645), tile-wide like the reference: the two
+                // `simd::all(...) continue` early-outs (:620, :623) span the non-sky lanes (pinned, see header).
+                const float reflectance = 0.5f;
+                float base[N][4], alphaRoughness[N], f0[N][3], diffuse[N][3], NoV[N], c[N][3];
+                V3 viewDir[N];
+                for (int i = 0; i < N; i++) {
+                    if (sky[i]) continue;
+                    unpack_srgb(surf[i].albedo, base[i]);
+                    alphaRoughness[i] = std::fmax(surf[i].roughness * surf[i].roughness, 1e-4f);
+                    float f0c = 0.16f * reflectance * reflectance;
+                    for (int k = 0; k < 3; k++) {
+                        f0[i][k] = lerpf(f0c, base[i][k], surf[i].metallic);
+                        diffuse[i][k] = base[i][k] * (1.0f - surf[i].metallic);
+                        c[i][k] = 0.0f;
+                    }
+                    viewDir[i] = normalize3({ view.x - worldPos[i].x, view.y - worldPos[i].y, view.z - worldPos[i].z });
+                    NoV[i] = std::fabs(dot3(surf[i].normal, viewDir[i])) + 1e-5f;
+                }
+                for (uint32_t li = 0; li < numLights; li++) {
+                    const swr_light& light = lights[li];
+                    V3 lightDir[N];
+                    float NoL[N], attenuation[N];
+                    bool allDark = true;
+                    for (int i = 0; i < N; i++) {
+                        if (sky[i]) continue;
+                        lightDir[i] = light.Type == 0 ? V3{ -light.Direction[0], -light.Direction[1], -light.Direction[2] }
+                                                      : normalize3({ light.Position[0] - worldPos[i].x, light.Position[1] - worldPos[i].y, light.Position[2] - worldPos[i].z });
+                        NoL[i] = dot3(surf[i].normal, lightDir[i]);
+                        allDark = allDark && (NoL[i] < 1e-4f);
+                    }
+                    if (allDark) continue;                                                   // :620
+                    bool allWeak = true;
+                    for (int i = 0; i < N; i++) {
+                        if (sky[i]) continue;
+                        attenuation[i] = light_attenuation(light, worldPos[i]) * light.Intensity * lightExposure;
+                        allWeak = allWeak && (NoL[i] * attenuation[i] < 1e-4f);
+                    }
+                    if (allWeak) continue;                                                   // :623
+                    for (int i = 0; i < N; i++) {
+                        if (sky[i]) continue;
+                        V3 halfway = normalize3({ viewDir[i].x + lightDir[i].x, viewDir[i].y + lightDir[i].y, viewDir[i].z + lightDir[i].z });
+                        float NoH = clampf(dot3(surf[i].normal, halfway), 0.0f, 1.0f);
+                        float LoH = clampf(dot3(lightDir[i], halfway), 0.0f, 1.0f);
+                        float D = D_GGX(NoH, alphaRoughness[i]);
+                        float V = V_SmithGGXCorrelatedFast(NoV[i], NoL[i], alphaRoughness[i]);
+                        float weight = std::fmax(NoL[i] * attenuation[i], 0.0f);
+                        for (int k = 0; k < 3; k++) {
+                            float F = F_Schlick1(LoH, f0[i][k]);
+                            float Fr = (D * V) * F;
+                            float Fd = diffuse[i][k] * kInvPi;
+                            c[i][k] += (Fd + Fr) * light.Color[k] * weight;
+                        }
+                    }
+                }
+                for (int i = 0; i < N; i++) {
+                    if (sky[i]) continue;
+                    for (int k = 0; k < 3; k++) outColor[i][k] = c[i][k] + base[i][k] * 0.05f;   // :642
+                }
+            }
+            // tonemap + pack (:680-688, Tonemap_Unreal :221-226)
+            for (int i = 0; i < N; i++) {
+                float o[3];
+                for (int k = 0; k < 3; k++) {
+                    float x = outColor[i][k] * exposure;
+                    o[k] = x / (x + 0.155f) * 1.019f;
+                }
+                tileData[i] = pack_rgba8(o[0], o[1], o[2], 1.0f);
+            }
+        }
+    }
+}
+
+// Texture2D::GenerateMip for one layer/level (Texture.h:577-596): 2x2 box filter in float, RNE pack.
+void orc_generate_mip(uint32_t* data, const swr_texture_desc* t, uint32_t layer, uint32_t level) {
+    uint32_t w = t->Width >> level, h = t->Height >> level;
+    const uint32_t* src = data + layer * t->LayerStride + t->MipOffsets[level - 1];
+    uint32_t* dst = data + layer * t->LayerStride + t->MipOffsets[level];
+    uint32_t sstride = t->RowShift - level + 1, dstride = t->RowShift - level;
+    const float s = 1.0f / 255;
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            uint32_t c[4] = { src[texel_offset(2 * x, 2 * y, sstride)], src[texel_offset(2 * x + 1, 2 * y, sstride)],
+                              src[texel_offset(2 * x, 2 * y + 1, sstride)], src[texel_offset(2 * x + 1, 2 * y + 1, sstride)] };
+            float avg[4];
+            for (int k = 0; k < 4; k++) {
+                float a = (float)((c[0] >> (8 * k)) & 255) * s, b = (float)((c[1] >> (8 * k)) & 255) * s;
+                float cc = (float)((c[2] >> (8 * k)) & 255) * s, d = (float)((c[3] >> (8 * k)) & 255) * s;
+                avg[k] = (((a + b) + cc) + d) * 0.25f;
+            }
+            dst[texel_offset(x, y, dstride)] = pack_rgba8(avg[0], avg[1], avg[2], avg[3]);
+        }
+}
+
+}  // extern "C"

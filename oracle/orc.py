@@ -74,6 +74,49 @@ def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, co
     return counters
 
 
+class _TextureDesc(C.Structure):   # swr_texture_desc (include/swr_types.h)
+    _fields_ = [("Width", C.c_uint32), ("Height", C.c_uint32), ("MipLevels", C.c_uint32), ("NumLayers", C.c_uint32),
+                ("RowShift", C.c_uint32), ("LayerStride", C.c_uint32), ("MipOffsets", C.c_uint32 * 16),
+                ("Data", C.c_void_p)]
+
+
+def _texture_descs(textures):
+    descs = (_TextureDesc * max(len(textures), 1))()
+    keep = []
+    for i, t in enumerate(textures):
+        data = np.ascontiguousarray(t.data, dtype=np.uint32)
+        keep.append(data)
+        d = descs[i]
+        d.Width, d.Height, d.MipLevels, d.NumLayers = t.width, t.height, t.mip_levels, t.num_layers
+        d.RowShift, d.LayerStride = t.row_shift, t.layer_stride
+        for k in range(16):
+            d.MipOffsets[k] = int(t.mip_offsets[k])
+        d.Data = data.ctypes.data
+    return descs, keep
+
+
+def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, object_to_clip, object_to_world3,
+            inv_screen_proj, view_pos, exposure: float = 1.0, **_unused):
+    """ShadingContext::Resolve on the CPU: layer 0 (surface ids) is overwritten with RGBA8 colour."""
+    assert meshlets.dtype.itemsize == 1728
+    descs, keep = _texture_descs(textures)
+    vp = np.ascontiguousarray(np.asarray(view_pos, dtype=np.float32))
+    o2w = np.ascontiguousarray(np.asarray(object_to_world3, dtype=np.float32).reshape(9))
+    lights = np.ascontiguousarray(lights)
+    lib().orc_resolve(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
+                      _p(materials) if len(materials) else None, descs, _p(lights) if len(lights) else None,
+                      C.c_uint32(len(lights)), _p(_mat(object_to_clip)), _p(o2w), _p(_mat(inv_screen_proj)), _p(vp),
+                      C.c_float(exposure))
+
+
+def generate_mip(tex, layer: int, level: int):
+    """Texture2D::GenerateMip on the CPU oracle (validates glimpsw_b200.textures.generate_mips)."""
+    descs, keep = _texture_descs([tex])
+    data = keep[0]
+    lib().orc_generate_mip(_p(data), descs, C.c_uint32(layer), C.c_uint32(level))
+    return data
+
+
 def frustum_planes(proj, view, model) -> np.ndarray:
     out = np.zeros((6, 4), dtype=np.float32)
     lib().orc_frustum_planes(_p(_mat(proj)), _p(_mat(view)), _p(_mat(model)), _p(out))
