@@ -47,6 +47,7 @@ EXPORTS = [
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
+    "swrb_alloc_pinned", "swrb_free_pinned",
 ]
 
 
@@ -217,6 +218,7 @@ class Rasterizer:
         self.lib = load_library()
         self._h = C.c_void_p()
         self._children = weakref.WeakSet()   # framebuffers / scenes must die before the device
+        self._pinned = []
         _check(self.lib.swrb_device_create(C.c_int(cuda_device), C.byref(self._h)))
         self.set_flags(enable_binning, enable_clipping, enable_guardband, fused_frustum_cull)
 
@@ -346,6 +348,16 @@ class Rasterizer:
         _check(self.lib.swrb_get_stage_times(self._h, t, n))
         return {k: (float(t[i]), int(n[i])) for i, k in enumerate(STAGE_NAMES)}
 
+    def alloc_pinned(self, shape, dtype) -> np.ndarray:
+        """A numpy array backed by cudaMallocHost memory (freed with the device)."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        ptr = C.c_void_p()
+        _check(self.lib.swrb_alloc_pinned(self._h, C.c_uint64(max(count * dtype.itemsize, 1)), C.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * (count * dtype.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
     def launch_count(self) -> int:
         v = C.c_uint64(0)
         _check(self.lib.swrb_get_launch_count(self._h, C.byref(v)))
@@ -355,6 +367,9 @@ class Rasterizer:
         if self._h:
             for child in list(self._children):
                 child.destroy()
+            for ptr in self._pinned:
+                self.lib.swrb_free_pinned(self._h, ptr)
+            self._pinned = []
             self.lib.swrb_device_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -783,6 +783,20 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     return SWRB_OK;
 }
 
+// ---- pinned host memory ------------------------------------------------------------------------
+int swrb_alloc_pinned(swrb_device* d, uint64_t bytes, void** out) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaMallocHost(out, bytes));
+    return SWRB_OK;
+}
+int swrb_free_pinned(swrb_device* d, void* ptr) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaFreeHost(ptr));
+    return SWRB_OK;
+}
+
 // ---- timing ------------------------------------------------------------------------------------
 int swrb_timer_begin(swrb_device* d) {
     if (!d) return fail(SWRB_E_INVALID, "device is null");

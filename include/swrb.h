@@ -133,6 +133,10 @@ SWRB_API int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_ho
 /* ShadingContext::Resolve (Shading.cpp:658-689): overwrites layer 0 with RGBA8 colour. */
 SWRB_API int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* uniforms);
 
+/* ---- pinned host staging (cudaMallocHost) for callers that want full-rate PCIe copies ------ */
+SWRB_API int swrb_alloc_pinned(swrb_device* dev, uint64_t bytes, void** out);
+SWRB_API int swrb_free_pinned(swrb_device* dev, void* ptr);
+
 /* ---- timing helpers (CUDA events on the device's stream; used by bench.py) ------------- */
 SWRB_API int swrb_timer_begin(swrb_device* dev);
 SWRB_API int swrb_timer_end(swrb_device* dev, float* elapsed_ms);    /* synchronises */

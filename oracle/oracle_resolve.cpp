@@ -213,17 +213,19 @@ extern "C" {
 
 // ShadingContext::Resolve over the whole framebuffer. color/depth are the 4x4-tiled layers 0/1;
 // layer 0 holds surface ids on entry and RGBA8 colour on exit (Shading.cpp:688).
-void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
-                 const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
-                 const swr_light* lights, uint32_t numLights,
-                 const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
-                 const float* viewPos, float exposure) {
+// Rows [yBegin, yEnd) (multiples of 4) only, so the threaded baseline can split the pass like
+// Rasterizer::Dispatch does (Rasterizer.cpp:822-846).
+void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                      const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                      const swr_light* lights, uint32_t numLights,
+                      const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                      const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd) {
     const float scaleU = 2.0f / (float)width, scaleV = 2.0f / (float)height;       // Rasterizer.h:226
     const float centerU = 0.5f * scaleU - 1.0f, centerV = 0.5f * scaleV - 1.0f;    // :227
     const V3 view = { viewPos[0], viewPos[1], viewPos[2] };
     const float lightExposure = exposure * 0.001f;                                  // Shading.cpp:674
 
-    for (uint32_t y0 = 0; y0 < height; y0 += 4) {
+    for (uint32_t y0 = yBegin; y0 < yEnd && y0 < height; y0 += 4) {
         for (uint32_t x0 = 0; x0 < width; x0 += 4) {
             uint32_t tileOffset = ((x0 & ~3u) << 2) + (y0 & ~3u) * width;           // Rasterizer.h:50-56
             const float* tileDepth = depth + tileOffset;
@@ -428,6 +430,15 @@ void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t h
             }
         }
     }
+}
+
+void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                 const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                 const swr_light* lights, uint32_t numLights,
+                 const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                 const float* viewPos, float exposure) {
+    orc_resolve_rows(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
+                     objectToWorld3, invScreenProj, viewPos, exposure, 0, height);
 }
 
 // Texture2D::GenerateMip for one layer/level (Texture.h:577-596): 2x2 box filter in float, RNE pack.

@@ -117,6 +117,53 @@ def generate_mip(tex, layer: int, level: int):
     return data
 
 
+class Baseline:
+    """Threaded AVX-512 restatement of the reference's binned CPU path (baseline_mt.cpp) — the timed CPU baseline."""
+
+    def __init__(self, threads: int = 0):
+        lib().orc_mt_create.restype = C.c_void_p
+        self._h = C.c_void_p(lib().orc_mt_create(C.c_int(threads)))
+        self.threads = int(lib().orc_mt_threads(self._h))
+        self.avx512 = bool(lib().orc_mt_uses_avx512(self._h))
+
+    def clear(self, fb: Framebuffer, color: int, depth: float):
+        bits = int(np.float32(depth).view(np.uint32))
+        lib().orc_mt_clear(self._h, _p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width * fb.height), C.c_uint32(color), C.c_uint32(bits))
+
+    def draw_meshlets(self, fb: Framebuffer, meshlets, meshlet_offset, count, object_to_clip, cull_bitmap=None,
+                      materials=None, guardband=True, counters=None):
+        if counters is None:
+            counters = np.zeros(4, dtype=np.uint64)
+        cb = None if cull_bitmap is None else _p(np.ascontiguousarray(cull_bitmap, dtype=np.uint16))
+        mats = None if materials is None or len(materials) == 0 else _p(materials)
+        lib().orc_mt_draw_meshlets(self._h, _p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height),
+                                   _p(meshlets), C.c_uint32(meshlet_offset), C.c_uint32(count), _p(_mat(object_to_clip)),
+                                   cb, mats, C.c_uint32(1 if guardband else 0), _p(counters))
+        return counters
+
+    def resolve(self, fb: Framebuffer, meshlets, materials, textures, lights, object_to_clip, object_to_world3,
+                inv_screen_proj, view_pos, exposure: float = 1.0, **_unused):
+        descs, keep = _texture_descs(textures)
+        vp = np.ascontiguousarray(np.asarray(view_pos, dtype=np.float32))
+        o2w = np.ascontiguousarray(np.asarray(object_to_world3, dtype=np.float32).reshape(9))
+        lights = np.ascontiguousarray(lights)
+        lib().orc_mt_resolve(self._h, _p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height),
+                             _p(meshlets), _p(materials) if len(materials) else None, descs,
+                             _p(lights) if len(lights) else None, C.c_uint32(len(lights)), _p(_mat(object_to_clip)),
+                             _p(o2w), _p(_mat(inv_screen_proj)), _p(vp), C.c_float(exposure))
+
+    def close(self):
+        if self._h:
+            lib().orc_mt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def frustum_planes(proj, view, model) -> np.ndarray:
     out = np.zeros((6, 4), dtype=np.float32)
     lib().orc_frustum_planes(_p(_mat(proj)), _p(_mat(view)), _p(_mat(model)), _p(out))
