@@ -401,6 +401,46 @@ def torus_knot_scene(nu: int = 300, nv: int = 120, width: int = 1920, height: in
                      materials=materials, textures=texs, lights=lights)
 
 
+def room_scene(width: int = 1920, height: int = 1080, subdiv: int = 5, size: float = 10.0, seed: int = 21) -> SceneData:
+    """Sponza-like stress for the big-triangle paths: the camera stands inside a box whose faces are coarse
+    grids (triangles hundreds of pixels wide, several crossing the near plane or leaving the guard band, which
+    the binned path counts as clipped and drops, Rasterizer.cpp:567-569) plus a few pillars of small triangles."""
+    faces = []
+    s = size
+    lin = np.linspace(-s, s, subdiv + 1)
+    a, b = np.meshgrid(lin, lin, indexing="ij")
+    one = np.ones_like(a)
+    for axis, sign in ((0, 1), (0, -1), (1, 1), (1, -1), (2, 1), (2, -1)):
+        coords = [a, b]
+        coords.insert(axis, one * sign * s)
+        P = np.stack(coords, -1).reshape(-1, 3)
+        n = subdiv + 1
+        ii, jj = np.meshgrid(np.arange(subdiv), np.arange(subdiv), indexing="ij")
+        v00, v01, v10, v11 = ii * n + jj, ii * n + jj + 1, (ii + 1) * n + jj, (ii + 1) * n + jj + 1
+        t = np.stack([np.stack([v00, v10, v01], -1), np.stack([v01, v10, v11], -1)], 2).reshape(-1, 3)
+        # inward-facing: pick the winding whose normal points to the origin
+        nrm = np.cross(P[t[0, 1]] - P[t[0, 0]], P[t[0, 2]] - P[t[0, 0]])
+        if np.dot(nrm, -P[t[0, 0]]) < 0:   # (this renderer's front faces have det > 0 with y pointing down-screen)
+            t = t[:, [0, 2, 1]]
+        faces.append(meshletize(P, t))
+    # pillars: thin boxes of many small triangles
+    r = rand01(seed, 64).reshape(-1, 4)
+    for k in range(8):
+        cx, cz = (r[k, 0] - 0.5) * 1.4 * s, (r[k, 1] - 0.5) * 1.4 * s
+        hgt = np.linspace(-s, s, 40)
+        ang = np.linspace(0, 2 * math.pi, 13)
+        A, H = np.meshgrid(ang, hgt, indexing="ij")
+        P = np.stack([cx + 0.5 * np.cos(A), H, cz + 0.5 * np.sin(A)], -1).reshape(-1, 3)
+        n = len(hgt)
+        ii, jj = np.meshgrid(np.arange(len(ang) - 1), np.arange(n - 1), indexing="ij")
+        v00, v01, v10, v11 = ii * n + jj, ii * n + jj + 1, (ii + 1) * n + jj, (ii + 1) * n + jj + 1
+        t = np.stack([np.stack([v00, v01, v10], -1), np.stack([v01, v11, v10], -1)], 2).reshape(-1, 3)
+        faces.append(meshletize(P, t))
+    meshlets = concat_meshlets(faces)
+    camera = cam.Camera(position=(1.0, -7.5, 2.0), euler=(0.7, 0.1), fov_deg=90.0, aspect=width / height)
+    return SceneData(f"room{subdiv}", meshlets, [DrawNode(0, len(meshlets), cam.identity())], camera, width, height)
+
+
 def resolve_uniforms(scene: SceneData, node: DrawNode, exposure: float = 1.0) -> dict:
     """The ShadingContext fields Resolve reads (Shading.h:21-33, Shading.cpp:659)."""
     proj, view = scene.view_proj()

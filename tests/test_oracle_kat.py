@@ -1,0 +1,215 @@
+"""Known-answer tests that pin the CPU oracle to the reference's arithmetic (CPU only).
+
+The reference ships no golden vectors, so the expected values here are derived by hand
+from the reference SOURCE — the fill rule of ComputeEdge (Rasterizer.cpp:291-295), the packed-s16
+bounding box with its carry quirk (:331-351), the guard-band classification
+(:353-397), the reverse-Z strict depth test (Shading.cpp:311-313) and the one-worker draw order — not
+from the oracle's own output. tests/golden/ additionally pins whole-frame hashes (regression only).
+"""
+import numpy as np
+import pytest
+
+from glimpsw_b200.layout import MESHLET_DTYPE, MATERIAL_DTYPE, NO_MATERIAL, detile
+
+IDENT = np.eye(4, dtype=np.float32)
+
+
+def meshlet_from_clip_tris(tris, material_id=NO_MATERIAL):
+    """One meshlet whose object-space positions ARE the clip-space xyz (w = 1 through the identity matrix)."""
+    tris = np.asarray(tris, dtype=np.float32)          # [T, 3, 3]
+    m = np.zeros(1, dtype=MESHLET_DTYPE)
+    verts = tris.reshape(-1, 3)
+    assert len(verts) <= 64
+    m["NumVertices"], m["NumTriangles"] = len(verts), len(tris)
+    m["AlphaCutoff"], m["MaterialId"] = 255, material_id
+    m["Positions"][0, :, : len(verts)] = verts.T
+    idx = np.arange(len(verts), dtype=np.uint8).reshape(-1, 3)
+    m["Indices"][0, :, : len(tris)] = idx.T
+    return m
+
+
+def fixed_to_ndc(fx, fy, w, h):
+    """28.4 fixed-point viewport coordinates (relative to the screen centre) -> exact NDC floats."""
+    return fx / float((w // 2) * 16), fy / float((h // 2) * 16)
+
+
+def px_to_fixed(px, py, w, h):
+    """Pixel-space position (pixel centres at +0.5) -> 28.4 fixed coordinates relative to the centre."""
+    return (px - w / 2) * 16, (py - h / 2) * 16
+
+
+def tri_px(points_px, w, h, z=0.5):
+    out = []
+    for (x, y) in points_px:
+        fx, fy = px_to_fixed(x, y, w, h)
+        nx, ny = fixed_to_ndc(fx, fy, w, h)
+        out.append((nx, ny, z))
+    return out
+
+
+def render(orc, tris, w=32, h=32, materials=None, material_id=NO_MATERIAL, guardband=True):
+    fb = orc.Framebuffer(w, h)
+    fb.clear(0xFFFFFFFF, 0.0)
+    m = meshlet_from_clip_tris(tris, material_id)
+    c = orc.draw_meshlets(fb, m, 0, 1, IDENT, materials=materials, guardband=guardband)
+    ids = detile(fb.data[0], w, h)
+    depth = detile(fb.data[1], w, h).view(np.float32)
+    return ids, depth, c
+
+
+def test_layouts():
+    assert MESHLET_DTYPE.itemsize == 1728
+    for name, off in dict(BoundCenter=0, BoundRadius=12, ConeApex=16, ConeAxis=28, ConeCutoff=40, NumVertices=44,
+                          NumTriangles=45, AlphaCutoff=46, MaterialId=48, TangentHandedness=56, Positions=64,
+                          TexCoords=832, NormalTangents=1088, Indices=1344).items():
+        assert MESHLET_DTYPE.fields[name][1] == off     # Scene.h:15-30
+
+
+def test_pixel_aligned_square_is_watertight(orc):
+    """Two triangles sharing a diagonal through pixel centres: every pixel of [8,24)^2 exactly once."""
+    w = h = 32
+    a = tri_px([(8, 8), (8, 24), (24, 8)], w, h)
+    b = tri_px([(24, 8), (8, 24), (24, 24)], w, h)
+    ids, depth, c = render(orc, [a, b], w, h)
+    covered = ids != 0xFFFFFFFF
+    expect = np.zeros((h, w), bool)
+    expect[8:24, 8:24] = True
+    assert np.array_equal(covered, expect)
+    only_a, _, _ = render(orc, [a], w, h)
+    only_b, _, _ = render(orc, [b], w, h)
+    assert not np.any((only_a != 0xFFFFFFFF) & (only_b != 0xFFFFFFFF))     # no pixel belongs to both
+    assert int(c[1]) == 2 and int(c[0]) == 2
+    assert np.all(depth[covered] == np.float32(0.5))                        # constant z, w = 1 -> depth == z exactly
+
+
+def test_top_left_rule_on_pixel_centres(orc):
+    """Edges through pixel centres: left/top inclusive, right/bottom exclusive (ComputeEdge bias)."""
+    w = h = 32
+    a = tri_px([(8.5, 8.5), (8.5, 24.5), (24.5, 8.5)], w, h)
+    b = tri_px([(24.5, 8.5), (8.5, 24.5), (24.5, 24.5)], w, h)
+    ids, _, _ = render(orc, [a, b], w, h)
+    covered = ids != 0xFFFFFFFF
+    expect = np.zeros((h, w), bool)
+    expect[8:24, 8:24] = True          # centres 8.5..23.5 in, 24.5 out
+    assert np.array_equal(covered, expect)
+
+
+def test_backface_and_double_sided(orc):
+    w = h = 32
+    ccw = tri_px([(8, 8), (8, 24), (24, 8)], w, h)
+    cw = [ccw[0], ccw[2], ccw[1]]
+    ids, _, c = render(orc, [cw], w, h)
+    assert not np.any(ids != 0xFFFFFFFF) and int(c[1]) == 0               # FrontCCW culls it (Rasterizer.cpp:264-270)
+    mats = np.zeros(1, dtype=MATERIAL_DTYPE)
+    mats["IsDoubleSided"], mats["AlphaCutoff"] = 1, 255
+    ids2, _, c2 = render(orc, [cw], w, h, materials=mats, material_id=0)
+    ids3, _, _ = render(orc, [ccw], w, h)
+    assert np.array_equal(ids2 != 0xFFFFFFFF, ids3 != 0xFFFFFFFF) and int(c2[1]) == 1   # same coverage either winding
+
+
+def test_strict_depth_first_wins_and_nearer_wins(orc):
+    w = h = 32
+    t = tri_px([(4, 4), (4, 28), (28, 4)], w, h, z=0.25)
+    ids, depth, _ = render(orc, [t, t], w, h)
+    assert set(np.unique(ids)) == {0, 0xFFFFFFFF}                          # equal depth: the first triangle stays
+    near = tri_px([(4, 4), (4, 28), (28, 4)], w, h, z=0.75)                # reverse-Z: larger = nearer
+    ids, depth, _ = render(orc, [near, t], w, h)
+    assert set(np.unique(ids)) == {0, 0xFFFFFFFF} and np.all(depth[ids == 0] == np.float32(0.75))
+    ids, depth, _ = render(orc, [t, near], w, h)
+    assert set(np.unique(ids)) == {1, 0xFFFFFFFF}
+
+
+def test_zero_and_negative_depth_never_pass(orc):
+    w = h = 32
+    for z in (0.0, -0.25):
+        ids, _, c = render(orc, [tri_px([(4, 4), (4, 28), (28, 4)], w, h, z=z)], w, h)
+        assert not np.any(ids != 0xFFFFFFFF)                               # Depth > 0.0 fails (Shading.cpp:311)
+        assert int(c[1]) == 1                                              # ... but it was set up and counted
+
+
+def test_bbox_carry_quirk_drops_a_row(orc):
+    """x_min in [-7,-1] (28.4) carries into y; with (y_min+8) % 16 == 0 the box starts one
+    pixel late, and after the &~3 alignment a whole 4-row band is skipped when (row % 4) == 3."""
+    w, h = 32, 36                                                          # halfH = 18 -> 18 % 4 == 2
+    def fx_tri(xmin):
+        pts = [(xmin, 24), (xmin, 24 + 16 * 6), (xmin + 16 * 6, 24)]       # top edge on the centres of pixel row 19
+        return [(*fixed_to_ndc(x, y, w, h), 0.5) for (x, y) in pts]
+    probe = orc.probe_triangle(np.array([[*v, 1.0] for v in fx_tri(-3)]), w, h)
+    assert int(probe["bbox"][0] >> 16) == 20                               # ideal box would start at row 16 (19 & ~3)
+    ids, _, _ = render(orc, [fx_tri(-3)], w, h)
+    ids_ok, _, _ = render(orc, [fx_tri(-8)], w, h)                         # x_min = -8: no carry
+    assert not np.any(ids[19] != 0xFFFFFFFF)                               # row 19 lost to the quirk
+    assert np.any(ids_ok[19] != 0xFFFFFFFF)                                # ... and present without it
+    assert np.any(ids[20:] != 0xFFFFFFFF)                                  # the rest of the triangle is still drawn
+
+
+def test_guard_band_and_clip_classification(orc):
+    w, h = 1920, 1080
+    bx = np.float32(2896.0) / np.float32(w)
+    inside = [(-0.5, -0.5, 0.5), (-0.5, 0.5, 0.5), (0.5, -0.5, 0.5)]
+    _, _, c = render(orc, [inside], w, h)
+    assert [int(c[1]), int(c[2])] == [1, 0]
+    # one vertex outside the viewport but inside the guard band: still trivially accepted
+    gb = [(-0.5, -0.5, 0.5), (-0.5, 0.5, 0.5), (float(bx) * 0.99, -0.5, 0.5)]
+    _, _, c = render(orc, [gb], w, h)
+    assert [int(c[1]), int(c[2])] == [1, 0]
+    # beyond the guard band: visible but non-trivial -> counted as clipped and dropped (Rasterizer.cpp:567-569)
+    out = [(-0.5, -0.5, 0.5), (-0.5, 0.5, 0.5), (float(bx) * 1.01, -0.5, 0.5)]
+    ids, _, c = render(orc, [out], w, h)
+    assert [int(c[1]), int(c[2])] == [0, 1] and not np.any(ids != 0xFFFFFFFF)
+    # with the guard band disabled (unbinned path, EnableGuardband = false) the first of those is non-trivial too
+    _, _, c = render(orc, [gb], w, h, guardband=False)
+    assert [int(c[1]), int(c[2])] == [0, 1]
+    # all three vertices left of the frustum: trivially rejected, not counted as clipped
+    left = [(-1.5, -0.5, 0.5), (-1.5, 0.5, 0.5), (-1.2, -0.5, 0.5)]
+    _, _, c = render(orc, [left], w, h)
+    assert [int(c[1]), int(c[2])] == [0, 0]
+    # a vertex past the z planes (|z| > w): near/far outcode -> non-trivial even though x,y are inside
+    zout = [(-0.5, -0.5, 0.5), (-0.5, 0.5, 0.5), (0.5, -0.5, 1.5)]
+    _, _, c = render(orc, [zout], w, h)
+    assert [int(c[1]), int(c[2])] == [0, 1]
+
+
+def test_coarse_raster_benchmark_triangles(orc):
+    """The three hand-written triangles of Benchmarks/CoarseRaster.cpp:380-395 at 64x64 and 32x32 (inputs from
+    the reference, expected coverage from geometry: exact areas of pixel-centre sampling)."""
+    tris = [[(-1, -1), (0, 1), (1, -1)], [(-1, -1), (-1, 1), (1, -1)], [(-1, -1), (1, 1), (0.2, -0.2)]]
+    mats = np.zeros(1, dtype=MATERIAL_DTYPE)
+    mats["IsDoubleSided"], mats["AlphaCutoff"] = 1, 255                    # FaceCullMode::None in the benchmark
+    for size in (64, 32):
+        for t, expected in zip(tris[:2], (size * size // 2, None)):
+            ids, _, c = render(orc, [[(x, y, 0.5) for (x, y) in t]], size, size, materials=mats, material_id=0)
+            n = int((ids != 0xFFFFFFFF).sum())
+            assert int(c[1]) == 1
+            if expected is not None:
+                assert n == expected                                        # isoceles: exactly half the screen
+            else:
+                assert n == size * (size - 1) // 2 or n == size * (size + 1) // 2   # right triangle: diagonal goes one way
+
+
+def test_cull_meshlets_planes_and_bitmap(orc):
+    from glimpsw_b200 import scenes, camera as cam
+    scene = scenes.instanced_scene(subdivisions=2, instances=27)
+    proj, view = scene.view_proj()
+    total_visible = 0
+    for node in scene.nodes[:6]:
+        planes = orc.frustum_planes(proj, view, node.model)
+        ms = scene.meshlets[node.meshlet_offset:node.meshlet_offset + node.meshlet_count]
+        bitmap, n = orc.cull_meshlets(ms, planes)
+        bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[: len(ms)]
+        assert bits.sum() == n
+        # independent float64 check of the same plane test (tolerant: only clearly in/out spheres are compared)
+        m = cam.object_to_clip(proj, view, node.model).astype(np.float64).T
+        c = np.concatenate([ms["BoundCenter"].astype(np.float64), np.ones((len(ms), 1))], 1)
+        r = ms["BoundRadius"].astype(np.float64)
+        ok = np.ones(len(ms), bool)
+        margin = np.full(len(ms), np.inf)
+        for row, sign in ((0, 1), (0, -1), (1, 1), (1, -1), (2, 1)):
+            p = m[3] + sign * m[row]
+            d = (c @ p) / np.linalg.norm(p[:3])
+            ok &= d > -r
+            margin = np.minimum(margin, np.abs(d + r))
+        sure = margin > 1e-3
+        assert np.array_equal(bits[sure].astype(bool), ok[sure])
+        total_visible += n
+    assert total_visible > 0
