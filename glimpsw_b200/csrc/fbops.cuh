@@ -37,18 +37,24 @@ k_keys_fill(ulonglong2* __restrict__ keys, uint32_t depthBits, uint32_t numVec2)
 }
 
 // Direct path, end of a draw: write depth + surface id of every pixel this draw won (FS_EncodeSurfaceId's
-// masked stores, Shading.cpp:328-330).
+// masked stores, Shading.cpp:328-330). With clearAll the framebuffer was logically cleared before the
+// draw, so every pixel is written (lost pixels get clearColor and the seed's depth = the clear depth).
 __global__ void __launch_bounds__(256)
-k_keys_unpack(const ulonglong2* __restrict__ keys, uint4* __restrict__ color, uint4* __restrict__ depth, uint32_t numVec) {
+k_keys_unpack(const ulonglong2* __restrict__ keys, uint4* __restrict__ color, uint4* __restrict__ depth, uint32_t numVec,
+              int clearAll, uint32_t clearColor) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
         ulonglong2 k0 = keys[2 * i], k1 = keys[2 * i + 1];
         uint32_t l0 = (uint32_t)k0.x, l1 = (uint32_t)k0.y, l2 = (uint32_t)k1.x, l3 = (uint32_t)k1.y;
-        if ((l0 & l1 & l2 & l3) == kKeySeed) continue;      // nothing won in these 4 pixels
-        uint4 c = color[i], d = depth[i];
-        if (l0 != kKeySeed) { c.x = kKeyIdBase - l0; d.x = (uint32_t)(k0.x >> 32); }
-        if (l1 != kKeySeed) { c.y = kKeyIdBase - l1; d.y = (uint32_t)(k0.y >> 32); }
-        if (l2 != kKeySeed) { c.z = kKeyIdBase - l2; d.z = (uint32_t)(k1.x >> 32); }
-        if (l3 != kKeySeed) { c.w = kKeyIdBase - l3; d.w = (uint32_t)(k1.y >> 32); }
+        bool anyWon = (l0 & l1 & l2 & l3) != kKeySeed;
+        if (!anyWon && !clearAll) continue;                  // nothing won in these 4 pixels
+        bool allWon = l0 != kKeySeed && l1 != kKeySeed && l2 != kKeySeed && l3 != kKeySeed;
+        uint4 c = make_uint4(clearColor, clearColor, clearColor, clearColor);
+        if (!clearAll && !allWon) c = color[i];
+        uint4 d = make_uint4((uint32_t)(k0.x >> 32), (uint32_t)(k0.y >> 32), (uint32_t)(k1.x >> 32), (uint32_t)(k1.y >> 32));
+        if (l0 != kKeySeed) c.x = kKeyIdBase - l0;
+        if (l1 != kKeySeed) c.y = kKeyIdBase - l1;
+        if (l2 != kKeySeed) c.z = kKeyIdBase - l2;
+        if (l3 != kKeySeed) c.w = kKeyIdBase - l3;
         color[i] = c; depth[i] = d;
     }
 }

@@ -1,5 +1,5 @@
-// mesh.cuh — K1: meshlet cull-bit/frustum test + mesh shading + clip classification + early
-// triangle setup, one warp per meshlet.
+// mesh.cuh — K1: meshlet cull-bit/frustum test + mesh shading + clip classification + triangle setup
+// + inline rasterization of small triangles, one warp per meshlet.
 //
 // Replaces (reference, one worker iteration of Rasterizer::DrawMeshlets, Rasterizer.cpp:535-594):
 //   ShadeMeshlet                 Shading.cpp:281-307   (cull bit, SoA position transform, index copy)
@@ -7,20 +7,28 @@
 //   GatherPos / index widen      Rasterizer.cpp:143-151, :553-558
 //   Clipper::ComputeClipCodes    Rasterizer.cpp:353-397
 //   TrianglePacket::Setup + bbox Rasterizer.cpp:257-289, :331-351
+// and, for triangles whose pixel region is at most kInlineMaxArea pixels, also
+//   TriangleEdgeVars::Setup      Rasterizer.cpp:296-329
+//   DrawTriangle<> + FS_EncodeSurfaceId<false>   Rasterizer.h:250-328, Shading.cpp:309-331
 //
 // Data flow per warp: 6 coalesced 128-byte position loads (lane L owns vertices L and L+32) and 24
-// 128-bit index loads; per-VERTEX perspective divide / snap / outcodes are computed once and parked
-// in shared memory (the CPU recomputes them per triangle corner; same inputs -> same bits); each lane
-// then sets up triangles L, L+32, L+64, L+96 through a shared-memory 64-entry remap. Survivors are
-// compacted with warp ballots and written as 32-byte records; in binned mode the same pass also
-// counts triangles per 32x32 screen tile.
+// 128-bit index loads; per-VERTEX perspective divide / snap / outcodes are computed once and parked in
+// shared memory (the CPU recomputes them per triangle corner; same inputs -> same bits); each lane then
+// sets up triangles L, L+32, L+64, L+96 through a shared-memory 64-entry remap.
+//   * Small triangles (the bulk of a meshlet scene) never leave the SM: the lane rasterizes them and
+//     reduces 64-bit depth|id keys straight into the frame's key buffer with REDG.MAX.64 — no triangle
+//     record, no bin entry, no second kernel touches them.
+//   * Larger triangles are appended to a per-warp list in shared memory; after the loop the warp takes
+//     one slice of the global record array (one atomic per meshlet), writes 32-byte records and, on the
+//     binned path, counts them per 32x32-px screen tile (pass 1 of the binner).
 #pragma once
 
 #include "common.cuh"
 
 namespace swrb {
 
-constexpr int kMeshWarps = 8;   // warps (= meshlets in flight) per block
+constexpr int kMeshWarps = 8;        // warps (= meshlets in flight) per block
+constexpr int kInlineMaxArea = 32;   // pixel-region size a lane rasterizes itself
 
 struct MeshWarpSmem {
     float nx[64], ny[64];       // NDC x, y (for the float determinant)
@@ -28,6 +36,7 @@ struct MeshWarpSmem {
     uint32_t pos[64];           // packed 28.4 x | y << 16
     uint32_t flags[64];         // bits 0-5 Cohen-Sutherland outcodes, bit 6 inside guard band
     uint32_t idx[96];           // Indices[3][128] as bytes
+    uint8_t deferred[128];      // prims that need a record (too large to rasterize inline)
 };
 
 __device__ __forceinline__ const DrawItem& find_draw(const DrawItem* draws, uint32_t numDraws, uint32_t work) {
@@ -47,10 +56,31 @@ __device__ __forceinline__ void count_single_tile(uint32_t* tileCount, bool acti
     if ((uint32_t)(__ffs(peers) - 1) == lane_id()) atomicAdd(&tileCount[tile], (uint32_t)__popc(peers));
 }
 
+// Rasterize a small triangle from registers into the key buffer (one lane).
+__device__ __forceinline__ void raster_inline(const TriRecord& t, const BBox& r, const FrameParams& fp, unsigned long long* keys) {
+    Edges e;
+    edge_setup(t, fp.halfW, fp.halfH, e);
+    uint32_t rowE0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)r.minX + (uint32_t)e.b12 * (uint32_t)r.minY;
+    uint32_t rowE1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)r.minX + (uint32_t)e.b20 * (uint32_t)r.minY;
+    uint32_t rowE2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)r.minX + (uint32_t)e.b01 * (uint32_t)r.minY;
+    for (int32_t y = r.minY; y < r.maxY; y++) {
+        uint32_t e0 = rowE0, e1 = rowE1, e2 = rowE2;
+        for (int32_t x = r.minX; x < r.maxX; x++) {
+            if ((int32_t)(e0 | e1 | e2) >= 0) {                                   // Rasterizer.h:289-290
+                float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);               // :296
+                if (d > 0.0f) atomicMax(keys + fb_pixel_offset((uint32_t)x, (uint32_t)y, fp.width), make_key(d, t.id));
+            }
+            e0 += (uint32_t)e.a12; e1 += (uint32_t)e.a20; e2 += (uint32_t)e.a01;
+        }
+        rowE0 += (uint32_t)e.b12; rowE1 += (uint32_t)e.b20; rowE2 += (uint32_t)e.b01;
+    }
+}
+
 template <bool kBinned>
-__global__ void __launch_bounds__(kMeshWarps * 32)
+__global__ void __launch_bounds__(kMeshWarps * 32, 3)
 k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
              const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
+             unsigned long long* __restrict__ keys,
              TriRecord* __restrict__ tris, TriRecordW* __restrict__ trisW, uint32_t triCapacity,
              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, DevCtl* __restrict__ ctl) {
     __shared__ MeshWarpSmem smem[kMeshWarps];
@@ -69,8 +99,8 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             if (((word >> (meshIdx & 15u)) & 1u) == 0) continue;
         }
         const swr_meshlet* m = meshlets + (d.meshletOffset + meshIdx);
-        const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(m));            // BoundCenter, BoundRadius
         if (d.fusedCull) {                                                      // Shading.cpp:803-809
+            const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(m));        // BoundCenter, BoundRadius
             float cx = __uint_as_float(hdrA.x), cy = __uint_as_float(hdrA.y), cz = __uint_as_float(hdrA.z);
             float rad = __uint_as_float(hdrA.w);
             bool vis = true;
@@ -81,8 +111,21 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             }
             if (!vis) continue;
         }
-        const uint4 hdrB = __ldg(reinterpret_cast<const uint4*>(m) + 2);        // bytes 32..47: ConeAxis.yz, ConeCutoff, counts
+        // issue every load of the meshlet before anything depends on them
+        const uint4 hdrB = __ldg(reinterpret_cast<const uint4*>(m) + 2);        // bytes 32..47: ..., NumVertices, NumTriangles, AlphaCutoff
         const uint32_t materialId = __ldg(reinterpret_cast<const uint32_t*>(m) + 12);
+        uint4 idxWord = make_uint4(0, 0, 0, 0);
+        if (lane < 24) idxWord = __ldg(reinterpret_cast<const uint4*>(m->Indices) + lane);   // Shading.cpp:300
+        float px[2], py[2], pz[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t v = lane + h * 32;
+            px[h] = __ldg(&m->Positions[0][v]); py[h] = __ldg(&m->Positions[1][v]); pz[h] = __ldg(&m->Positions[2][v]);
+        }
+        float M[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) M[i] = d.M[i];
+
         const uint32_t numVerts = hdrB.w & 0xFFu, numTris = (hdrB.w >> 8) & 0xFFu;
         const uint32_t primCount = min(numTris, 128u);
         if (primCount == 0) continue;
@@ -94,9 +137,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             cullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
             fsId = mat.AlphaCutoff < 255 ? 1u : 0u;
         }
-
-        // ---- index copy: 24 x 128-bit loads (Shading.cpp:300)
-        if (lane < 24) reinterpret_cast<uint4*>(s.idx)[lane] = __ldg(reinterpret_cast<const uint4*>(m->Indices) + lane);
+        if (lane < 24) reinterpret_cast<uint4*>(s.idx)[lane] = idxWord;
 
         // ---- transform + per-vertex setup: lane owns vertices lane and lane+32
         const uint32_t vertSlots = min((numVerts + 15u) & ~15u, 64u);           // reference walks 16-wide vectors
@@ -104,12 +145,12 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
         for (int h = 0; h < 2; h++) {
             uint32_t v = lane + h * 32;
             if (v < vertSlots) {
-                float x = __ldg(&m->Positions[0][v]), y = __ldg(&m->Positions[1][v]), z = __ldg(&m->Positions[2][v]);
+                float x = px[h], y = py[h], z = pz[h];
                 // simd::mul(mat4, (pos,1)) — SIMD.h:457-464
-                float cx = __fmaf_rn(x, d.M[0], __fmaf_rn(y, d.M[4], __fmaf_rn(z, d.M[8], d.M[12])));
-                float cy = __fmaf_rn(x, d.M[1], __fmaf_rn(y, d.M[5], __fmaf_rn(z, d.M[9], d.M[13])));
-                float cz = __fmaf_rn(x, d.M[2], __fmaf_rn(y, d.M[6], __fmaf_rn(z, d.M[10], d.M[14])));
-                float cw = __fmaf_rn(x, d.M[3], __fmaf_rn(y, d.M[7], __fmaf_rn(z, d.M[11], d.M[15])));
+                float cx = __fmaf_rn(x, M[0], __fmaf_rn(y, M[4], __fmaf_rn(z, M[8], M[12])));
+                float cy = __fmaf_rn(x, M[1], __fmaf_rn(y, M[5], __fmaf_rn(z, M[9], M[13])));
+                float cz = __fmaf_rn(x, M[2], __fmaf_rn(y, M[6], __fmaf_rn(z, M[10], M[14])));
+                float cw = __fmaf_rn(x, M[3], __fmaf_rn(y, M[7], __fmaf_rn(z, M[11], M[15])));
                 // ComputeClipCodes per vertex (Rasterizer.cpp:375-386)
                 uint32_t f = 0;
                 f |= (cx < -cw) ? 1u : 0u;
@@ -130,17 +171,14 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
         }
         __syncwarp();
 
-        // ---- triangles: lane owns prims lane + 32k
+        // ---- triangles: lane owns prims lane + 32k; small ones are rasterized right here
         const uint8_t* idx = reinterpret_cast<const uint8_t*>(s.idx);
-        TriRecord rec[4];
-        float recW[4][3];
-        uint32_t tileLo[4] = {1, 1, 1, 1}, tileHi[4] = {0, 0, 0, 0};   // empty range unless set below
-        uint32_t keepBits = 0;      // bit k: this lane's k-th triangle survives
-        uint32_t total = 0, myOffset[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t prim = lane + k * 32;
-            bool keep = false, nonTrivial = false;
+        const uint32_t idBase = (d.meshletOffset + meshIdx) * SWR_MAX_PRIMS;
+        uint32_t numDeferred = 0;
+#pragma unroll 1
+        for (uint32_t k = 0; k < 4 && k * 32 < primCount; k++) {
+            const uint32_t prim = lane + k * 32;
+            bool keep = false, nonTrivial = false, defer = false;
             if (prim < primCount) {
                 uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
                 uint32_t f0 = s.flags[i0], f1 = s.flags[i1], f2 = s.flags[i2];
@@ -162,57 +200,66 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     ref_render_bbox(p0, p1, p2, fp.halfW, fp.halfH, bbMin, bbMax);
                     keep = det > 0.0f && lo16(bbMin) < lo16(bbMax) && hi16(bbMin) < hi16(bbMax);   // :269, :283
                     if (keep) {
-                        rec[k].pos0 = p0; rec[k].pos1 = p1; rec[k].pos2 = p2;
-                        rec[k].z0 = s.z[i0]; rec[k].z1 = s.z[i1]; rec[k].z2 = s.z[i2];
-                        rec[k].id = (d.meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;
-                        rec[k].aux = fsId;
-                        if (fsId) { recW[k][0] = s.rw[i0]; recW[k][1] = s.rw[i1]; recW[k][2] = s.rw[i2]; }
-                        if (kBinned) {
-                            BBox r;
-                            if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {
-                                tileLo[k] = (uint32_t)(r.minX >> kTileShift) | ((uint32_t)(r.minY >> kTileShift) << 16);
-                                tileHi[k] = (uint32_t)((r.maxX - 1) >> kTileShift) | ((uint32_t)((r.maxY - 1) >> kTileShift) << 16);
-                            }   // else: counted as rasterized (the reference does) but touches no pixel
+                        BBox r;
+                        if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {     // else: counted, touches no pixel
+                            if (fsId == 0 && (r.maxX - r.minX) * (r.maxY - r.minY) <= kInlineMaxArea) {
+                                TriRecord t;
+                                t.pos0 = p0; t.pos1 = p1; t.pos2 = p2;
+                                t.z0 = s.z[i0]; t.z1 = s.z[i1]; t.z2 = s.z[i2];
+                                t.id = idBase + prim; t.aux = 0;
+                                raster_inline(t, r, fp, keys);
+                            } else {
+                                defer = true;
+                            }
                         }
                     }
                 }
             }
-            uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
-            uint32_t clipMask = __ballot_sync(0xFFFFFFFFu, nonTrivial);
-            myOffset[k] = total + __popc(keepMask & ((1u << lane) - 1u));
-            total += __popc(keepMask);
-            if (keep) keepBits |= 1u << k;
+            const uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
+            const uint32_t clipMask = __ballot_sync(0xFFFFFFFFu, nonTrivial);
+            const uint32_t deferMask = __ballot_sync(0xFFFFFFFFu, defer);
+            if (defer) s.deferred[numDeferred + __popc(deferMask & ((1u << lane) - 1u))] = (uint8_t)prim;
+            numDeferred += __popc(deferMask);
             if (lane == 0) { nRasterized += __popc(keepMask); nClipped += __popc(clipMask); }   // :579, :568
         }
 
-        // ---- compact + write records (one atomic per meshlet)
-        uint32_t base = 0;
-        if (lane == 0 && total > 0) base = atomicAdd(&ctl->triCount, total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        bool fits = base + total <= triCapacity;
-        if (!fits && lane == 0) atomicExch(&ctl->overflow, 1u);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            bool keep = (keepBits >> k) & 1u;
-            uint32_t slot = base + myOffset[k];
-            if (keep && fits) {
-                uint4* dst = reinterpret_cast<uint4*>(tris + slot);
-                dst[0] = make_uint4(rec[k].pos0, rec[k].pos1, rec[k].pos2, __float_as_uint(rec[k].z0));
-                dst[1] = make_uint4(__float_as_uint(rec[k].z1), __float_as_uint(rec[k].z2), rec[k].id, rec[k].aux);
-                if (rec[k].aux & 1u) *reinterpret_cast<float4*>(trisW + slot) = make_float4(recW[k][0], recW[k][1], recW[k][2], 0.0f);
-            }
-            if (kBinned) {
-                // per-tile counting: one-tile triangles are warp-aggregated, the rest loop over their tiles
-                uint32_t tx0 = tileLo[k] & 0xFFFFu, ty0 = tileLo[k] >> 16, tx1 = tileHi[k] & 0xFFFFu, ty1 = tileHi[k] >> 16;
-                bool valid = keep && fits && tx0 <= tx1 && ty0 <= ty1;
-                uint32_t nTiles = valid ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
-                count_single_tile(tileCount, nTiles == 1, ty0 * fp.tilesX + tx0);
-                if (nTiles > (uint32_t)kBigTriTileLimit) {
-                    uint32_t b = atomicAdd(&ctl->bigCount, 1u);
-                    bigList[b] = slot;          // capacity == triCapacity
-                } else if (nTiles > 1) {
-                    for (uint32_t ty = ty0; ty <= ty1; ty++)
-                        for (uint32_t tx = tx0; tx <= tx1; tx++) atomicAdd(&tileCount[ty * fp.tilesX + tx], 1u);
+        // ---- deferred (larger) triangles: one slice of the record array per meshlet
+        if (numDeferred) {
+            __syncwarp();
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->triCount, numDeferred);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const bool fits = base + numDeferred <= triCapacity;
+            if (!fits && lane == 0) atomicExch(&ctl->overflow, 1u);
+            for (uint32_t j0 = 0; j0 < numDeferred; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const bool active = fits && j < numDeferred;
+                uint32_t tx0 = 1, ty0 = 1, tx1 = 0, ty1 = 0;
+                const uint32_t slot = base + j;
+                if (active) {
+                    const uint32_t prim = s.deferred[j];
+                    uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
+                    uint32_t p0 = s.pos[i0], p1 = s.pos[i1], p2 = s.pos[i2];
+                    uint4* dst = reinterpret_cast<uint4*>(tris + slot);
+                    dst[0] = make_uint4(p0, p1, p2, __float_as_uint(s.z[i0]));
+                    dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), idBase + prim, fsId);
+                    if (fsId) *reinterpret_cast<float4*>(trisW + slot) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], 0.0f);
+                    if (kBinned) {
+                        BBox r;
+                        raster_region(p0, p1, p2, fp.halfW, fp.halfH, r);
+                        tx0 = (uint32_t)(r.minX >> kTileShift); ty0 = (uint32_t)(r.minY >> kTileShift);
+                        tx1 = (uint32_t)((r.maxX - 1) >> kTileShift); ty1 = (uint32_t)((r.maxY - 1) >> kTileShift);
+                    }
+                }
+                if (kBinned) {   // pass 1 of the binner: per-tile counts
+                    const uint32_t nTiles = (active && tx0 <= tx1 && ty0 <= ty1) ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
+                    count_single_tile(tileCount, nTiles == 1, ty0 * fp.tilesX + tx0);
+                    if (nTiles > (uint32_t)kBigTriTileLimit) {
+                        bigList[atomicAdd(&ctl->bigCount, 1u)] = slot;     // capacity == triCapacity
+                    } else if (nTiles > 1) {
+                        for (uint32_t ty = ty0; ty <= ty1; ty++)
+                            for (uint32_t tx = tx0; tx <= tx1; tx++) atomicAdd(&tileCount[ty * fp.tilesX + tx], 1u);
+                    }
                 }
             }
         }

@@ -675,12 +675,24 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     // transient counters (triCount, bigCount, binTotal keep `overflow` sticky until the host reads it)
     CU(cudaMemsetAsync(d->ctl, 0, offsetof(DevCtl, overflow), d->stream));
 
-    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 8);
+    // ---- key buffer: seeds = the depth every pixel has before this draw (or the pending clear's depth)
+    if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
+    const int clearMode = fb->pendingClear ? 1 : 0;
+    {
+        StageScope ss(d, SWRB_STAGE_CLEAR);
+        if (clearMode)
+            k_keys_fill<<<grid_for(d, numVec * 2, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), fb->clearDepthBits, numVec * 2);
+        else
+            k_keys_init<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const uint4*>(depthLayer), reinterpret_cast<ulonglong2*>(fb->keys), numVec);
+        d->launches++;
+    }
+
+    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 6);
     if (binned) {
         CU(cudaMemsetAsync(d->tileCount, 0, (size_t)numTiles * 4, d->stream));
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp,
+            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
                                                                            d->tris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, d->ctl);
             d->launches++;
         }
@@ -692,34 +704,29 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
-            int clearMode = fb->pendingClear ? 1 : 0;
-            k_tile_raster<<<numTiles, kTileThreads, 0, d->stream>>>(d->tris, d->tileOffset, d->binEntries, d->bigList, fp, colorLayer, depthLayer,
-                                                                    clearMode, fb->clearColor, fb->clearDepthBits, d->ctl);
+            k_tile_raster<<<numTiles, kTileThreads, 0, d->stream>>>(d->tris, d->tileOffset, d->binEntries, d->bigList, fp, fb->keys, colorLayer, depthLayer,
+                                                                    clearMode, fb->clearColor, d->ctl);
             d->launches++;
-            // on overflow the tile kernel returns without touching the framebuffer, so the recorded
-            // clear has to survive; otherwise it has just been performed.
-            // (overflow is detected at the next synchronising call, which reports an error.)
-            fb->pendingClear = false;
         }
     } else {
-        if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp,
+            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
                                                                             d->tris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr, d->ctl);
             d->launches++;
         }
-        rc = fb_materialize_clear(fb);
-        if (rc) return rc;
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
-            k_keys_init<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const uint4*>(depthLayer), reinterpret_cast<ulonglong2*>(fb->keys), numVec);
             k_raster_direct<<<grid_for(d, d->triCap, 256, 8), 256, 0, d->stream>>>(d->tris, fp, fb->keys, d->bigItems, (uint32_t)std::min<uint64_t>(d->bigItemCap, 0xFFFFFFFFu), d->ctl);
             k_raster_big<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
-            k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const ulonglong2*>(fb->keys), reinterpret_cast<uint4*>(colorLayer), reinterpret_cast<uint4*>(depthLayer), numVec);
-            d->launches += 4;
+            k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const ulonglong2*>(fb->keys), reinterpret_cast<uint4*>(colorLayer), reinterpret_cast<uint4*>(depthLayer), numVec,
+                                                                             clearMode, fb->clearColor);
+            d->launches += 3;
         }
     }
+    // The recorded clear has now been performed by the tile / unpack pass. (If a work list overflowed the
+    // draw was aborted on the device and the next synchronising call reports SWRB_E_BIN_OVERFLOW.)
+    fb->pendingClear = false;
     CU(cudaGetLastError());
     return SWRB_OK;
 }

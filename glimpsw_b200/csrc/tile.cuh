@@ -109,13 +109,17 @@ __device__ __forceinline__ void tile_raster_warp(const TriRecord& t, const Frame
     }
 }
 
-// clearMode: 0 = load the tile's depth from the framebuffer; 1 = framebuffer is freshly cleared to
-// (clearColor, clearDepthBits) and this kernel performs the clear for the tile as part of its store.
+// The tile is staged from the frame's 64-bit key buffer, which already holds the seeds (pre-draw depth)
+// and every small triangle the mesh kernel rasterized inline; this kernel adds the binned triangles and
+// is also the pass that turns keys back into the framebuffer's depth and surface-id layers.
+// clearMode: 0 = only pixels this draw won are written; 1 = the framebuffer was logically cleared to
+// (clearColor, clear depth = the seeds' depth) and this kernel performs that clear as part of its store.
 __global__ void __launch_bounds__(kTileThreads)
 k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ tileOffset,
               const uint32_t* __restrict__ binEntries, const uint32_t* __restrict__ bigList, FrameParams fp,
+              const unsigned long long* __restrict__ keysGlobal,
               uint32_t* __restrict__ colorLayer, uint32_t* __restrict__ depthLayer,
-              int clearMode, uint32_t clearColor, uint32_t clearDepthBits, DevCtl* __restrict__ ctl) {
+              int clearMode, uint32_t clearColor, DevCtl* __restrict__ ctl) {
     __shared__ __align__(16) unsigned long long keys[kTilePixels];
     __shared__ uint32_t wideList[kTileThreads];
     __shared__ uint32_t wideCount;
@@ -127,7 +131,6 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
     const int32_t tileX0 = (int32_t)(tx << kTileShift), tileY0 = (int32_t)(ty << kTileShift);
     const uint32_t listBegin = tileOffset[tile], listEnd = tileOffset[tile + 1];
     const uint32_t numBig = ctl->bigCount;
-    if (clearMode == 0 && listBegin == listEnd && numBig == 0) return;   // nothing can change in this tile
 
     // ---- stage the tile: thread owns 4 consecutive pixels (one row of a 4x4 fragment)
     const uint32_t fr = tid >> 5, l4 = (tid & 31u) * 4u;                 // fragment row, first of 4 pixels in it
@@ -135,13 +138,13 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
     const bool inFb = gx < fp.width && gy < fp.height;
     const uint32_t gOff = fb_pixel_offset(gx, gy, fp.width);
     {
-        uint4 d = make_uint4(clearDepthBits, clearDepthBits, clearDepthBits, clearDepthBits);
-        if (clearMode == 0 && inFb) d = *reinterpret_cast<const uint4*>(depthLayer + gOff);
-        unsigned long long* k = keys + fr * 128u + l4;
-        k[0] = ((unsigned long long)d.x << 32) | kKeySeed;
-        k[1] = ((unsigned long long)d.y << 32) | kKeySeed;
-        k[2] = ((unsigned long long)d.z << 32) | kKeySeed;
-        k[3] = ((unsigned long long)d.w << 32) | kKeySeed;
+        ulonglong2 a = make_ulonglong2(kKeySeed, kKeySeed), b = a;
+        if (inFb) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(keysGlobal + gOff);
+            a = __ldcg(src); b = __ldcg(src + 1);      // written with L2 atomics by the mesh kernel
+        }
+        ulonglong2* k = reinterpret_cast<ulonglong2*>(keys + fr * 128u + l4);
+        k[0] = a; k[1] = b;
     }
     if (tid == 0) wideCount = 0;
     __syncthreads();

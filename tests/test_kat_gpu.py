@@ -51,7 +51,7 @@ def test_guard_band_giants_and_int32_wrap(orc, rast_factory, binning):
     rast = rast_factory(enable_binning=binning)
     w, h = 1920, 1080
     mats = np.zeros(1, dtype=MATERIAL_DTYPE)
-    mats["IsDoubleSided"], mats["AlphaCutoff"] = 1, 255
+    mats["IsDoubleSided"], mats["AlphaCutoff"], mats["TextureId"] = 1, 255, -1
     tris = [[(-1.5, -2.6, 0.3), (1.5, -2.6, 0.3), (0.0, 2.6, 0.3)],
             [(-1.5, 2.6, 0.5), (1.5, 2.67, 0.5), (1.5, -2.67, 0.6)],
             [(-1.49, -2.67, 0.2), (-1.49, 2.67, 0.7), (1.507, 0.0, 0.4)],
