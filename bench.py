@@ -119,8 +119,13 @@ def run_ours(args):
     node = scene.nodes[0]
     tris = scene.num_triangles
     rast = api.Rasterizer(local_rank, enable_binning=(args.mode == "binned"))
-    stream = torch.cuda.current_stream()
-    rast.set_stream(stream.cuda_stream)          # one in-order stream for our kernels, torch events and NCCL
+    # One in-order, non-default stream for our kernels, the torch timing events and NCCL. (torch's default
+    # stream has handle 0, which swrb_device_set_stream reads as "use your own stream": events recorded
+    # there would not be ordered with the kernels.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    rast.set_stream(stream.cuda_stream)
     gscene = rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)
     fb = rast.create_framebuffer(scene.width, scene.height)
     batch = rast.make_batch([dict(offset=node.meshlet_offset, count=node.meshlet_count, object_to_clip=scene.object_to_clip(node))])
@@ -253,6 +258,7 @@ def run_ours(args):
                        "l2": "flushed (256 MB write) before every timed step, outside the step's events",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
             "frames_per_s": round(world / (ms_per_step * 1e-3), 1),
+            "step_ms_min_median_max": [round(float(np.min(step_ms)), 5), round(float(np.median(step_ms)), 5), round(float(np.max(step_ms)), 5)],
             "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(scene.meshlets.nbytes + 512),

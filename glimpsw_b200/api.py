@@ -47,7 +47,7 @@ EXPORTS = [
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
-    "swrb_alloc_pinned", "swrb_free_pinned",
+    "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats",
 ]
 
 
@@ -362,6 +362,12 @@ class Rasterizer:
         v = C.c_uint64(0)
         _check(self.lib.swrb_get_launch_count(self._h, C.byref(v)))
         return int(v.value)
+
+    def draw_stats(self) -> dict:
+        """Work-list sizes of the last draw: triangle records, big-list entries, tile-list entries."""
+        out = (C.c_uint32 * 4)()
+        _check(self.lib.swrb_get_draw_stats(self._h, out))
+        return {"records": int(out[0]), "big": int(out[1]), "bin_entries": int(out[2])}
 
     def destroy(self):
         if self._h:

@@ -18,45 +18,59 @@ k_fb_clear(uint4* __restrict__ layerA, uint32_t valueA, uint4* __restrict__ laye
     }
 }
 
-// Direct path, start of a draw: keys <- (stored depth << 32 | seed). A pixel keeps its seed unless a
-// fragment of THIS draw passes the strict depth test, so earlier draws win ties like in the reference.
+// Start of a draw: seed the key buffer and reset the draw's transient device state in one launch.
+// keys <- (depth << 32 | seed), where depth is the pixel's stored depth (depthLayer != null) or the
+// pending clear's depth. A pixel keeps its seed unless a fragment of THIS draw passes the strict depth
+// test, so earlier draws win ties like in the reference. Also zeroes the per-tile counters and the work
+// counters in DevCtl (everything before `overflow`, which stays sticky until the host reads it).
 __global__ void __launch_bounds__(256)
-k_keys_init(const uint4* __restrict__ depth, ulonglong2* __restrict__ keys, uint32_t numVec) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
-        uint4 d = depth[i];
+k_frame_begin(const uint4* __restrict__ depthLayer, uint32_t clearDepthBits, ulonglong2* __restrict__ keys, uint32_t numVec,
+              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileCursor, uint32_t numTiles, DevCtl* __restrict__ ctl) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; }
+    for (uint32_t i = gid; i < numTiles; i += stride) { tileCount[i] = 0; tileCursor[i] = 0; }
+    for (uint32_t i = gid; i < numVec; i += stride) {
+        uint4 d = make_uint4(clearDepthBits, clearDepthBits, clearDepthBits, clearDepthBits);
+        if (depthLayer != nullptr) d = depthLayer[i];
         keys[2 * i + 0] = make_ulonglong2(((unsigned long long)d.x << 32) | kKeySeed, ((unsigned long long)d.y << 32) | kKeySeed);
         keys[2 * i + 1] = make_ulonglong2(((unsigned long long)d.z << 32) | kKeySeed, ((unsigned long long)d.w << 32) | kKeySeed);
     }
 }
-// Same, when the framebuffer was just cleared: no read.
-__global__ void __launch_bounds__(256)
-k_keys_fill(ulonglong2* __restrict__ keys, uint32_t depthBits, uint32_t numVec2) {
-    unsigned long long k = ((unsigned long long)depthBits << 32) | kKeySeed;
-    ulonglong2 v = make_ulonglong2(k, k);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec2; i += gridDim.x * blockDim.x) keys[i] = v;
-}
 
-// Direct path, end of a draw: write depth + surface id of every pixel this draw won (FS_EncodeSurfaceId's
+// Keys -> framebuffer layers: depth + surface id of every pixel the draw won (FS_EncodeSurfaceId's
 // masked stores, Shading.cpp:328-330). With clearAll the framebuffer was logically cleared before the
 // draw, so every pixel is written (lost pixels get clearColor and the seed's depth = the clear depth).
+// With depthOnly layer 0 is left alone (the resolve pass already replaced the ids by colour).
 __global__ void __launch_bounds__(256)
 k_keys_unpack(const ulonglong2* __restrict__ keys, uint4* __restrict__ color, uint4* __restrict__ depth, uint32_t numVec,
-              int clearAll, uint32_t clearColor) {
+              int clearAll, uint32_t clearColor, int depthOnly, const DevCtl* __restrict__ ctl) {
+    if (ctl->overflow) return;                                // the draw that produced these keys was aborted
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
         ulonglong2 k0 = keys[2 * i], k1 = keys[2 * i + 1];
         uint32_t l0 = (uint32_t)k0.x, l1 = (uint32_t)k0.y, l2 = (uint32_t)k1.x, l3 = (uint32_t)k1.y;
         bool anyWon = (l0 & l1 & l2 & l3) != kKeySeed;
         if (!anyWon && !clearAll) continue;                  // nothing won in these 4 pixels
+        depth[i] = make_uint4((uint32_t)(k0.x >> 32), (uint32_t)(k0.y >> 32), (uint32_t)(k1.x >> 32), (uint32_t)(k1.y >> 32));
+        if (depthOnly) continue;
         bool allWon = l0 != kKeySeed && l1 != kKeySeed && l2 != kKeySeed && l3 != kKeySeed;
         uint4 c = make_uint4(clearColor, clearColor, clearColor, clearColor);
         if (!clearAll && !allWon) c = color[i];
-        uint4 d = make_uint4((uint32_t)(k0.x >> 32), (uint32_t)(k0.y >> 32), (uint32_t)(k1.x >> 32), (uint32_t)(k1.y >> 32));
         if (l0 != kKeySeed) c.x = kKeyIdBase - l0;
         if (l1 != kKeySeed) c.y = kKeyIdBase - l1;
         if (l2 != kKeySeed) c.z = kKeyIdBase - l2;
         if (l3 != kKeySeed) c.w = kKeyIdBase - l3;
-        color[i] = c; depth[i] = d;
+        color[i] = c;
     }
+}
+
+// L2 eviction helper for benchmarks: streams `numVec` 128-bit words through the cache (read only).
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ src, uint32_t numVec, uint32_t* __restrict__ sink) {
+    uint32_t acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
+        uint4 v = __ldcg(src + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345679u) sink[0] = acc;   // never true for the 0x5A fill pattern; keeps the loads alive
 }
 
 // Framebuffer::GetPixels (ImageHelpers.cpp:109-147): 4x4-tiled layer -> row-major. One thread moves

@@ -18,8 +18,8 @@
 
 #include "common.cuh"
 #include "cull.cuh"
-#include "mesh.cuh"
 #include "bin.cuh"
+#include "mesh.cuh"
 #include "tile.cuh"
 #include "raster_direct.cuh"
 #include "fbops.cuh"
@@ -71,9 +71,10 @@ struct swrb_device {
     uint64_t binCap = 0;
     uint64_t reserveTris = 0, reserveBins = 0;
 
-    uint32_t* tileCount = nullptr;    // [numTiles] + offsets [numTiles+1] + cursors [numTiles]
+    uint32_t* tileCount = nullptr;    // [numTiles] + offsets [numTiles+1] + cursors [numTiles] + active list [numTiles]
     uint32_t* tileOffset = nullptr;
     uint32_t* tileCursor = nullptr;
+    uint32_t* activeTiles = nullptr;
     uint32_t tileCap = 0;
 
     DrawItem* drawItems = nullptr;    // device
@@ -104,6 +105,9 @@ struct swrb_device {
     StageTimer* st = nullptr;
     uint64_t launches = 0;
     uint64_t hostTimeNs[SWR_PERF_Count_] = {};
+    uint32_t lastTriCount = 0;            // records written by the most recent draw the host has read back
+    swrb_fb* lastFb = nullptr;            // target of the last draw (its lazy state is rolled back if that draw aborted)
+    bool lastFbPendingClear = false;
 };
 
 struct DeviceTexture {     // Texture2D<RGBA8u, TiledY8> (Texture.h:314-329)
@@ -131,8 +135,23 @@ struct swrb_fb {
     uint32_t* data = nullptr;
     unsigned long long* keys = nullptr;   // direct path only (lazily allocated)
     bool pendingClear = false;            // Clear() recorded but not yet materialised (fused into the next draw)
+    // Lazy vis-buffer: after a draw the result lives in `keys`; the depth / id layers are produced on demand.
+    bool visInKeys = false;               // keys hold the latest vis-buffer, layers are stale for pixels the draw won
+    bool keysClearMode = false;           // that draw started from a logically cleared framebuffer (seed = clear value)
+    uint32_t keysClearColor = 0;
+    bool layer0IsColor = false;           // resolve already consumed the keys and wrote colour to layer 0
     uint32_t clearColor = 0, clearDepthBits = 0;
 };
+
+// An aborted draw (device work list overflow) never touched the depth / id layers; every kernel after it
+// was predicated off by the sticky device flag. Drop its keys and restore the recorded clear, if any.
+static void rollback_aborted_draw(swrb_device* d) {
+    if (!d->lastFb) return;
+    d->lastFb->visInKeys = false;
+    d->lastFb->layer0IsColor = false;
+    d->lastFb->pendingClear = d->lastFbPendingClear;
+    d->lastFb = nullptr;
+}
 
 // ---------------------------------------------------------------------------------------------
 struct StageScope {
@@ -163,13 +182,17 @@ static int ensure_buffer(void** ptr, uint64_t* cap, uint64_t need, size_t elem) 
     return SWRB_OK;
 }
 
+static void rollback_aborted_draw(swrb_device* d);
+
 static int check_overflow(swrb_device* d) {
     // caller has synchronised the stream
     CU(cudaMemcpy(d->ctlHost, d->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost));
+    d->lastTriCount = d->ctlHost->triCount;
     if (d->ctlHost->overflow) {
         uint32_t which = d->ctlHost->overflow;
         uint32_t zero = 0;
         cudaMemcpy(&d->ctl->overflow, &zero, 4, cudaMemcpyHostToDevice);
+        rollback_aborted_draw(d);
         return fail(SWRB_E_BIN_OVERFLOW,
                     "device work list overflowed (%s); the draw was aborted before touching the framebuffer — "
                     "call swrb_device_reserve() with larger limits and redraw",
@@ -364,6 +387,7 @@ void swrb_fb_destroy(swrb_fb* fb) {
     if (!fb) return;
     cudaSetDevice(fb->dev->cudaDevice);
     cudaStreamSynchronize(fb->dev->stream);
+    if (fb->dev->lastFb == fb) fb->dev->lastFb = nullptr;
     cudaFree(fb->data); cudaFree(fb->keys);
     delete fb;
 }
@@ -387,10 +411,27 @@ static int fb_clear_layer_now(swrb_fb* fb, uint32_t layerA, uint32_t valueA, int
     return SWRB_OK;
 }
 
-static int fb_materialize_clear(swrb_fb* fb) {
-    if (!fb->pendingClear) return SWRB_OK;
-    fb->pendingClear = false;
-    return fb_clear_layer_now(fb, 0, fb->clearColor, 1, fb->clearDepthBits);
+// Brings layers 0/1 up to date: performs a recorded clear, or unpacks the last draw's keys.
+static int fb_materialize(swrb_fb* fb) {
+    swrb_device* d = fb->dev;
+    if (fb->pendingClear) {
+        fb->pendingClear = false;
+        int rc = fb_clear_layer_now(fb, 0, fb->clearColor, 1, fb->clearDepthBits);
+        if (rc) return rc;
+    }
+    if (fb->visInKeys) {
+        uint32_t numVec = fb->width * fb->height / 4;
+        StageScope ss(d, SWRB_STAGE_RASTER);
+        k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
+            reinterpret_cast<const ulonglong2*>(fb->keys), reinterpret_cast<uint4*>(fb->data),
+            reinterpret_cast<uint4*>(fb->data + fb->layerStride), numVec, fb->keysClearMode ? 1 : 0, fb->keysClearColor,
+            fb->layer0IsColor ? 1 : 0, d->ctl);
+        d->launches++;
+        CU(cudaGetLastError());
+        fb->visInKeys = false;
+        fb->layer0IsColor = false;
+    }
+    return SWRB_OK;
 }
 
 int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth) {
@@ -401,6 +442,8 @@ int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth) {
     uint32_t bits; memcpy(&bits, &depth, 4);
     if (bits == 0x80000000u) bits = 0;
     fb->pendingClear = true;
+    fb->visInKeys = false;
+    fb->layer0IsColor = false;
     fb->clearColor = color;
     fb->clearDepthBits = bits;
     return SWRB_OK;
@@ -410,7 +453,7 @@ int swrb_fb_clear_layer(swrb_fb* fb, uint32_t layer, uint32_t value) {
     if (!fb) return fail(SWRB_E_INVALID, "fb is null");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
     CU(cudaSetDevice(fb->dev->cudaDevice));
-    int rc = fb_materialize_clear(fb);
+    int rc = fb_materialize(fb);
     if (rc) return rc;
     return fb_clear_layer_now(fb, layer, value, -1, 0);
 }
@@ -419,7 +462,7 @@ int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host) {
     if (!fb || !dst_host) return fail(SWRB_E_INVALID, "null argument");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
     CU(cudaSetDevice(fb->dev->cudaDevice));
-    int rc = fb_materialize_clear(fb);
+    int rc = fb_materialize(fb);
     if (rc) return rc;
     CU(cudaMemcpyAsync(dst_host, fb->data + (size_t)layer * fb->layerStride, (size_t)fb->width * fb->height * 4, cudaMemcpyDeviceToHost, fb->dev->stream));
     CU(cudaStreamSynchronize(fb->dev->stream));
@@ -430,7 +473,7 @@ int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host) 
     if (!fb || !src_host) return fail(SWRB_E_INVALID, "null argument");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
     CU(cudaSetDevice(fb->dev->cudaDevice));
-    int rc = fb_materialize_clear(fb);
+    int rc = fb_materialize(fb);
     if (rc) return rc;
     CU(cudaMemcpyAsync(fb->data + (size_t)layer * fb->layerStride, src_host, (size_t)fb->width * fb->height * 4, cudaMemcpyHostToDevice, fb->dev->stream));
     CU(cudaStreamSynchronize(fb->dev->stream));
@@ -443,7 +486,7 @@ int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uin
     if (stride < fb->width || stride % 4) return fail(SWRB_E_INVALID, "stride %u must be >= width and a multiple of 4", stride);
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
-    int rc = fb_materialize_clear(fb);
+    int rc = fb_materialize(fb);
     if (rc) return rc;
     uint32_t numVec = fb->width * fb->height / 4;
     k_fb_detile<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
@@ -570,14 +613,12 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
     if (numTiles > d->tileCap) {
         if (d->tileCount) CU(cudaFree(d->tileCount));
         d->tileCount = nullptr;
-        CU(cudaMalloc(&d->tileCount, ((size_t)numTiles * 3 + 4) * 4));
-        d->tileOffset = d->tileCount + numTiles;
-        d->tileCursor = d->tileOffset + numTiles + 1;
+        CU(cudaMalloc(&d->tileCount, ((size_t)numTiles * 4 + 4) * 4));
         d->tileCap = numTiles;
-    } else {
-        d->tileOffset = d->tileCount + d->tileCap;
-        d->tileCursor = d->tileOffset + d->tileCap + 1;
     }
+    d->tileOffset = d->tileCount + d->tileCap;
+    d->tileCursor = d->tileOffset + d->tileCap + 1;
+    d->activeTiles = d->tileCursor + d->tileCap;
     return SWRB_OK;
 }
 
@@ -669,27 +710,28 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     FrameParams fp = frame_params(d, fb, binned);
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t numVec = fb->width * fb->height / 4;
-    uint32_t* colorLayer = fb->data;
     uint32_t* depthLayer = fb->data + fb->layerStride;
-
-    // transient counters (triCount, bigCount, binTotal keep `overflow` sticky until the host reads it)
-    CU(cudaMemsetAsync(d->ctl, 0, offsetof(DevCtl, overflow), d->stream));
 
     // ---- key buffer: seeds = the depth every pixel has before this draw (or the pending clear's depth)
     if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
+    if (fb->visInKeys) {           // an earlier draw's result is still only in the keys: the layers must be current to re-seed
+        rc = fb_materialize(fb);
+        if (rc) return rc;
+    }
     const int clearMode = fb->pendingClear ? 1 : 0;
     {
         StageScope ss(d, SWRB_STAGE_CLEAR);
-        if (clearMode)
-            k_keys_fill<<<grid_for(d, numVec * 2, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), fb->clearDepthBits, numVec * 2);
-        else
-            k_keys_init<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const uint4*>(depthLayer), reinterpret_cast<ulonglong2*>(fb->keys), numVec);
+        k_frame_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(clearMode ? nullptr : reinterpret_cast<const uint4*>(depthLayer), fb->clearDepthBits,
+                                                                         reinterpret_cast<ulonglong2*>(fb->keys), numVec, d->tileCount, d->tileCursor, numTiles, d->ctl);
         d->launches++;
     }
 
-    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 6);
+    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 4);      // 64 registers -> 4 resident blocks per SM
+    // record consumers are grid-stride loops over a device-side count; size their grids from the last count
+    // the host has seen (any grid is correct, a fitting one avoids launching a thousand idle blocks)
+    const uint64_t recEstimate = std::min<uint64_t>(d->triCap, std::max<uint64_t>(4096, 4 * (uint64_t)d->lastTriCount));
+    const uint32_t scatterGrid = grid_for(d, recEstimate, 256, 8);
     if (binned) {
-        CU(cudaMemsetAsync(d->tileCount, 0, (size_t)numTiles * 4, d->stream));
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
@@ -698,14 +740,15 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         }
         {
             StageScope ss(d, SWRB_STAGE_BIN);
-            k_tile_scan<<<1, 1024, 0, d->stream>>>(d->tileCount, d->tileOffset, d->tileCursor, numTiles, (uint32_t)std::min<uint64_t>(d->binCap, 0xFFFFFFFFu), d->ctl);
-            k_bin_scatter<<<grid_for(d, d->triCap, 256, 8), 256, 0, d->stream>>>(d->tris, fp, d->tileOffset, d->tileCursor, d->binEntries, d->ctl);
-            d->launches += 2;
+            k_bin_scatter<<<scatterGrid, kScatterThreads, (numTiles + 1) * sizeof(uint32_t), d->stream>>>(
+                d->tris, fp, d->tileCount, d->tileOffset, d->tileCursor, d->activeTiles, d->binEntries,
+                (uint32_t)std::min<uint64_t>(d->binCap, 0xFFFFFFFFu), d->ctl);
+            d->launches++;
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
-            k_tile_raster<<<numTiles, kTileThreads, 0, d->stream>>>(d->tris, d->tileOffset, d->binEntries, d->bigList, fp, fb->keys, colorLayer, depthLayer,
-                                                                    clearMode, fb->clearColor, d->ctl);
+            k_tile_raster<<<std::min<uint32_t>(numTiles, (uint32_t)d->numSMs * 4u), kTileThreads, 0, d->stream>>>(
+                d->tris, d->tileOffset, d->activeTiles, d->binEntries, d->bigList, fp, fb->keys, d->ctl);
             d->launches++;
         }
     } else {
@@ -717,15 +760,20 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
-            k_raster_direct<<<grid_for(d, d->triCap, 256, 8), 256, 0, d->stream>>>(d->tris, fp, fb->keys, d->bigItems, (uint32_t)std::min<uint64_t>(d->bigItemCap, 0xFFFFFFFFu), d->ctl);
+            k_raster_direct<<<scatterGrid, 256, 0, d->stream>>>(d->tris, fp, fb->keys, d->bigItems, (uint32_t)std::min<uint64_t>(d->bigItemCap, 0xFFFFFFFFu), d->ctl);
             k_raster_big<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
-            k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<const ulonglong2*>(fb->keys), reinterpret_cast<uint4*>(colorLayer), reinterpret_cast<uint4*>(depthLayer), numVec,
-                                                                             clearMode, fb->clearColor);
-            d->launches += 3;
+            d->launches += 2;
         }
     }
-    // The recorded clear has now been performed by the tile / unpack pass. (If a work list overflowed the
-    // draw was aborted on the device and the next synchronising call reports SWRB_E_BIN_OVERFLOW.)
+    // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the
+    // resolve pass reads the keys directly. If a work list overflowed, the draw was aborted on the device
+    // and the next synchronising call reports SWRB_E_BIN_OVERFLOW and rolls this state back.
+    d->lastFb = fb;
+    d->lastFbPendingClear = fb->pendingClear;
+    fb->visInKeys = true;
+    fb->keysClearMode = clearMode != 0;
+    fb->keysClearColor = fb->clearColor;
+    fb->layer0IsColor = false;
     fb->pendingClear = false;
     CU(cudaGetLastError());
     return SWRB_OK;
@@ -768,8 +816,11 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
-    int rc = fb_materialize_clear(fb);
-    if (rc) return rc;
+    const bool fromKeys = fb->visInKeys && !fb->layer0IsColor;
+    if (!fromKeys) {
+        int rc = fb_materialize(fb);
+        if (rc) return rc;
+    }
     ResolveParams rp;
     memcpy(rp.objectToClip, u->ObjectToClip, sizeof(rp.objectToClip));
     memcpy(rp.objectToWorld, u->ObjectToWorld, sizeof(rp.objectToWorld));
@@ -780,12 +831,15 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     rp.meshlets = scene->meshlets; rp.materials = scene->materials; rp.textures = scene->textures;
     rp.lights = scene->lights; rp.numLights = scene->numLights; rp.numMeshlets = scene->numMeshlets;
     rp.color = fb->data; rp.depth = fb->data + fb->layerStride;
+    rp.keys = fb->keys; rp.keysClearMode = fb->keysClearMode ? 1u : 0u; rp.clearColor = fb->keysClearColor;
     {
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
-        k_resolve<<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        if (fromKeys) k_resolve<true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        else k_resolve<false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
         d->launches++;
     }
+    if (fromKeys) fb->layer0IsColor = true;      // depth is still only in the keys
     CU(cudaGetLastError());
     return SWRB_OK;
 }
@@ -825,10 +879,16 @@ int swrb_flush_l2(swrb_device* d) {
     if (!d) return fail(SWRB_E_INVALID, "device is null");
     CU(cudaSetDevice(d->cudaDevice));
     if (!d->l2Scratch) {
-        d->l2ScratchBytes = (size_t)256 << 20;   // 2x the 126 MB L2
+        d->l2ScratchBytes = (size_t)512 << 20;   // two halves of 256 MB, each 2x the 126 MB L2
+        // (contents are irrelevant)
         CU(cudaMalloc(&d->l2Scratch, d->l2ScratchBytes));
     }
-    CU(cudaMemsetAsync(d->l2Scratch, 0x5A, d->l2ScratchBytes, d->stream));
+    // write 256 MB (evicts everything, leaves dirty scratch lines), then read a second 256 MB so that what
+    // stays in L2 is clean: the first timed kernel then pays for its own traffic, not for our write-backs
+    CU(cudaMemsetAsync(d->l2Scratch, 0x5A, d->l2ScratchBytes / 2, d->stream));
+    k_l2_read<<<d->numSMs * 8, 256, 0, d->stream>>>(reinterpret_cast<const uint4*>((const char*)d->l2Scratch + d->l2ScratchBytes / 2),
+                                                      (uint32_t)(d->l2ScratchBytes / 2 / 16), reinterpret_cast<uint32_t*>(d->l2Scratch));
+    CU(cudaGetLastError());
     return SWRB_OK;
 }
 
@@ -868,6 +928,16 @@ int swrb_get_stage_times(swrb_device* d, float out_us[SWRB_STAGE_COUNT_], uint32
 int swrb_get_launch_count(swrb_device* d, uint64_t* out) {
     if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
     *out = d->launches;
+    return SWRB_OK;
+}
+
+int swrb_get_draw_stats(swrb_device* d, uint32_t out[4]) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));
+    int rc = check_overflow(d);
+    if (rc) return rc;
+    out[0] = d->ctlHost->triCount; out[1] = d->ctlHost->bigCount; out[2] = d->ctlHost->binTotal; out[3] = 0;
     return SWRB_OK;
 }
 

@@ -110,27 +110,30 @@ __device__ __forceinline__ void tile_raster_warp(const TriRecord& t, const Frame
 }
 
 // The tile is staged from the frame's 64-bit key buffer, which already holds the seeds (pre-draw depth)
-// and every small triangle the mesh kernel rasterized inline; this kernel adds the binned triangles and
-// is also the pass that turns keys back into the framebuffer's depth and surface-id layers.
-// clearMode: 0 = only pixels this draw won are written; 1 = the framebuffer was logically cleared to
-// (clearColor, clear depth = the seeds' depth) and this kernel performs that clear as part of its store.
+// and every small triangle the mesh kernel rasterized inline; this kernel adds the tile's binned
+// triangles and stores the tile back with 128-bit coalesced writes (the key buffer shares the
+// framebuffer's 4x4-tiled pixel order). Tiles without binned triangles exit at once. Keys become the
+// depth / surface-id layers lazily (k_keys_unpack) or are consumed directly by the resolve pass.
 __global__ void __launch_bounds__(kTileThreads)
-k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ tileOffset,
+k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ tileOffset, const uint32_t* __restrict__ activeTiles,
               const uint32_t* __restrict__ binEntries, const uint32_t* __restrict__ bigList, FrameParams fp,
-              const unsigned long long* __restrict__ keysGlobal,
-              uint32_t* __restrict__ colorLayer, uint32_t* __restrict__ depthLayer,
-              int clearMode, uint32_t clearColor, DevCtl* __restrict__ ctl) {
+              unsigned long long* __restrict__ keysGlobal, DevCtl* __restrict__ ctl) {
     __shared__ __align__(16) unsigned long long keys[kTilePixels];
-    __shared__ uint32_t wideList[kTileThreads];
+    __shared__ uint4 wideRecs[kTileThreads][2];     // records of the chunk's triangles that need a whole warp
     __shared__ uint32_t wideCount;
 
     if (ctl->overflow) return;
     const uint32_t tid = threadIdx.x;
-    const uint32_t tile = blockIdx.x;
+    // persistent CTAs over the compacted list of tiles that have work (the launch order of a plain
+    // one-CTA-per-tile grid would park the busy tiles behind thousands of empty ones)
+    const uint32_t numActive = ctl->numActiveTiles;
+  for (uint32_t at = blockIdx.x; at < numActive; at += gridDim.x) {
+    const uint32_t tile = activeTiles[at];
     const uint32_t tx = tile % fp.tilesX, ty = tile / fp.tilesX;
     const int32_t tileX0 = (int32_t)(tx << kTileShift), tileY0 = (int32_t)(ty << kTileShift);
     const uint32_t listBegin = tileOffset[tile], listEnd = tileOffset[tile + 1];
     const uint32_t numBig = ctl->bigCount;
+    if (listBegin == listEnd && numBig == 0) continue;    // nothing binned here: the keys are already final
 
     // ---- stage the tile: thread owns 4 consecutive pixels (one row of a 4x4 fragment)
     const uint32_t fr = tid >> 5, l4 = (tid & 31u) * 4u;                 // fragment row, first of 4 pixels in it
@@ -162,42 +165,39 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
                 r.maxX = min(r.maxX, tileX0 + kTileSize); r.maxY = min(r.maxY, tileY0 + kTileSize);
                 int32_t w = r.maxX - r.minX, h = r.maxY - r.minY;
                 if (w > 0 && h > 0) {
-                    if (w * h <= kTileSmallArea) tile_raster_thread(t, r, fp, tileX0, tileY0, keys);
-                    else wideList[atomicAdd(&wideCount, 1u)] = triIdx;
+                    if (w * h <= kTileSmallArea) {
+                        tile_raster_thread(t, r, fp, tileX0, tileY0, keys);
+                    } else {   // park the record in shared memory for the warp-cooperative pass (no second global fetch)
+                        uint32_t slot = atomicAdd(&wideCount, 1u);
+                        wideRecs[slot][0] = make_uint4(t.pos0, t.pos1, t.pos2, __float_as_uint(t.z0));
+                        wideRecs[slot][1] = make_uint4(__float_as_uint(t.z1), __float_as_uint(t.z2), t.id, t.aux);
+                    }
                 }
             }
         }
         __syncthreads();
         const uint32_t nWide = wideCount;
         for (uint32_t w = tid >> 5; w < nWide; w += kTileThreads / 32) {
-            TriRecord t = load_record(tris, wideList[w]);
+            uint4 a = wideRecs[w][0], b = wideRecs[w][1];
+            TriRecord t;
+            t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
+            t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
             tile_raster_warp(t, fp, tileX0, tileY0, keys);
         }
         __syncthreads();
-        if (tid == 0) wideCount = 0;
-        __syncthreads();
+        if (tid == 0) wideCount = 0;      // ordered before the next chunk's atomics by the barrier after its loads
+        if (base + kTileThreads < total) __syncthreads();
     }
 
-    // ---- epilogue: 128-bit coalesced stores in the framebuffer's own 4x4-tiled order
+    // ---- epilogue: the tile goes back to the key buffer, 2 x 128-bit stores per thread, 1 KB per warp
     if (inFb) {
-        const unsigned long long* k = keys + fr * 128u + l4;
-        unsigned long long k0 = k[0], k1 = k[1], k2 = k[2], k3 = k[3];
-        uint32_t l0 = (uint32_t)k0, l1 = (uint32_t)k1, l2 = (uint32_t)k2, l3 = (uint32_t)k3;
-        bool anyWon = (l0 & l1 & l2 & l3) != kKeySeed;
-        if (anyWon || clearMode == 1) {
-            uint4 d = make_uint4((uint32_t)(k0 >> 32), (uint32_t)(k1 >> 32), (uint32_t)(k2 >> 32), (uint32_t)(k3 >> 32));
-            uint4 c = make_uint4(clearColor, clearColor, clearColor, clearColor);
-            bool allWon = l0 != kKeySeed && l1 != kKeySeed && l2 != kKeySeed && l3 != kKeySeed;
-            if (clearMode == 0 && !allWon) c = *reinterpret_cast<const uint4*>(colorLayer + gOff);
-            if (l0 != kKeySeed) c.x = kKeyIdBase - l0;
-            if (l1 != kKeySeed) c.y = kKeyIdBase - l1;
-            if (l2 != kKeySeed) c.z = kKeyIdBase - l2;
-            if (l3 != kKeySeed) c.w = kKeyIdBase - l3;
-            *reinterpret_cast<uint4*>(depthLayer + gOff) = d;
-            *reinterpret_cast<uint4*>(colorLayer + gOff) = c;
-        }
+        const ulonglong2* k = reinterpret_cast<const ulonglong2*>(keys + fr * 128u + l4);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(keysGlobal + gOff);
+        dst[0] = k[0]; dst[1] = k[1];
     }
     if (tid == 0 && listBegin != listEnd) atomicAdd(&ctl->perf[3], 1ull);   // BinQueueFlushes (Rasterizer.cpp:622)
+    __syncthreads();      // the shared tile is reused by the next active tile
+  }
 }
 
 }  // namespace swrb

@@ -148,6 +148,9 @@ enum { SWRB_STAGE_CLEAR = 0, SWRB_STAGE_CULL, SWRB_STAGE_MESH, SWRB_STAGE_BIN, S
 SWRB_API int swrb_device_enable_stage_timing(swrb_device* dev, int enable);
 SWRB_API int swrb_get_stage_times(swrb_device* dev, float out_us[SWRB_STAGE_COUNT_], uint32_t launches_out[SWRB_STAGE_COUNT_]);
 SWRB_API int swrb_get_launch_count(swrb_device* dev, uint64_t* out);  /* kernels launched since create */
+/* Work-list sizes of the last draw (synchronises): out = { triangle records written (triangles too large for
+ * the mesh kernel's inline raster), big-list entries, tile-list entries, reserved }. */
+SWRB_API int swrb_get_draw_stats(swrb_device* dev, uint32_t out[4]);
 
 #ifdef __cplusplus
 }
