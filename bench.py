@@ -47,9 +47,10 @@ def build_workload(rank: int = 0):
     scene.materials["AlphaCutoff"] = 255
     scene.textures = [tx.procedural_material_texture(1024, seed=2)]
     scene.lights = scenes.default_light()
-    if rank:   # every rank renders its own view of the same scene (small seeded camera offset)
+    if rank:   # every rank renders its own view of the same scene: a seeded sub-millimetre camera offset, so the
+        # views differ (different sub-pixel coverage) while the per-GPU work stays the same (weak scaling)
         r = scenes.rand01(100 + rank, 3)
-        scene.camera.position = scene.camera.position + (r - 0.5) * np.array([0.3, 0.1, 0.3])
+        scene.camera.position = scene.camera.position + (r - 0.5) * 0.004
     return scene
 
 
@@ -130,19 +131,61 @@ def run_ours(args):
     fb = rast.create_framebuffer(scene.width, scene.height)
     batch = rast.make_batch([dict(offset=node.meshlet_offset, count=node.meshlet_count, object_to_clip=scene.object_to_clip(node))])
     uni = scenes.resolve_uniforms(scene, node)
-    composite = torch.empty((scene.height, scene.width), dtype=torch.int32, device="cuda")
-    gathered = [torch.empty_like(composite) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # N > 1: the resolved composite of every view is gathered to rank 0 over NVLink. Default: the de-tile
+    # kernel of each rank stores straight into rank 0's buffer (peer memory, glimpsw_b200.sharding.PeerComposites)
+    # with device-side ready/ack signals; fallback (--gather nccl): NCCL gather on a side stream. Either way
+    # the exchange of frame k overlaps the render of frame k+1 (double-buffered) and the tail is timed.
+    from glimpsw_b200 import sharding
+    comm = torch.cuda.Stream() if world > 1 else None
+    gather_kind = "none"
+    peers = None
+    if world > 1:
+        gather_kind = args.gather
+        if gather_kind == "p2p":
+            try:
+                peers = sharding.PeerComposites(scene.height, scene.width, rank, world)
+            except Exception as exc:          # symmetric memory unavailable: use the collective
+                if rank == 0:
+                    print(f"bench.py: peer-memory gather unavailable ({exc!r}); using NCCL gather", file=sys.stderr)
+                gather_kind = "nccl"
+        flag = torch.tensor([1 if gather_kind == "p2p" else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks must agree
+        if int(flag.item()) == 0 and gather_kind == "p2p":
+            gather_kind, peers = "nccl", None
+    composites = [torch.empty((scene.height, scene.width), dtype=torch.int32, device="cuda") for _ in range(2)]
+    gathered = [[torch.empty_like(composites[0]) for _ in range(world)] for _ in range(2)] if (gather_kind == "nccl" and rank == 0) else [None, None]
+    rendered = [torch.cuda.Event() for _ in range(2)]
+    gather_done = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0}
+
+    resolved = torch.cuda.Event()
 
     def frame():
         fb.clear(0xFF000000, 0.0)
         rast.draw_prebuilt(fb, gscene, batch)
+        exchange = world > 1 and gather_kind != "none"
+        if exchange and state["k"] > 0:
+            stream.wait_event(gather_done[(state["k"] - 1) & 1])     # the previous frame's de-tile has read layer 0
         rast.resolve(fb, gscene, **uni)
-        if world > 1:   # composite gather over NVLink (views are independent: this is the only exchange step)
-            fb.get_pixels_device(0, composite.data_ptr())
-            dist.gather(composite, gathered, dst=0)
+        if exchange:
+            slot = state["k"] & 1
+            state["k"] += 1
+            resolved.record(stream)
+            with torch.cuda.stream(comm):                            # everything below runs beside the next frame's draw
+                comm.wait_event(resolved)
+                if peers is not None:
+                    peers.before_write(slot, comm)
+                    fb.get_pixels_device(0, peers.dst_ptr(slot), cuda_stream=comm.cuda_stream)   # GetPixels straight into rank 0's memory
+                    peers.after_write(slot, comm)
+                    peers.collect(slot, comm)
+                else:
+                    fb.get_pixels_device(0, composites[slot].data_ptr(), cuda_stream=comm.cuda_stream)
+                    dist.gather(composites[slot], gathered[slot], dst=0)
+                gather_done[slot].record(comm)
 
     def barrier():
         if world > 1:
+            comm.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -150,11 +193,12 @@ def run_ours(args):
         frame()
     barrier()
 
-    # ---- timed region: exactly K steps; L2 is flushed (256 MB write) before each step, outside its events
+    # ---- timed region: exactly K steps; L2 is flushed before each step, outside the step's events
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = rast.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     barrier()
     t_wall0 = time.perf_counter()
     for b, e in ev:
@@ -162,12 +206,17 @@ def run_ours(args):
         b.record(stream)
         frame()
         e.record(stream)
+    tail[0].record(stream)
+    if world > 1:                                                 # the last gathers are part of the job
+        stream.wait_event(gather_done[0])
+        stream.wait_event(gather_done[1])
+    tail[1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = rast.launch_count() - launches0
     clocks = sampler.stop()
     step_ms = [b.elapsed_time(e) for b, e in ev]
-    total_ms = float(sum(step_ms))
+    total_ms = float(sum(step_ms)) + tail[0].elapsed_time(tail[1])
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -254,8 +303,8 @@ def run_ours(args):
             "config": {"workload": "C2: procedural 999,600-triangle meshlet grid (10,200 meshlets), 1920x1080, "
                                    "clear + vis-buffer (depth + triangle id) + resolve (1 material, 1024^2 2-layer texture, 1 directional light)",
                        "triangles_per_frame": tris, "meshlets": len(scene.meshlets), "mode": args.mode,
-                       "parallelism": f"view-parallel x{world}" + (", NCCL gather of composites to rank 0 in the timed region" if world > 1 else ""),
-                       "l2": "flushed (256 MB write) before every timed step, outside the step's events",
+                       "parallelism": f"view-parallel x{world}" + ({"p2p": ", composites stored by each rank's de-tile kernel straight into rank 0's memory over NVLink (peer memory + device-side signals, double-buffered, tail included)", "nccl": ", composites gathered to rank 0 with NCCL on a side stream (double-buffered, tail included)", "none": ""}[gather_kind]),
+                       "l2": "evicted (256 MB write + 256 MB read) before every timed step, outside the step's events",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
             "frames_per_s": round(world / (ms_per_step * 1e-3), 1),
             "step_ms_min_median_max": [round(float(np.min(step_ms)), 5), round(float(np.median(step_ms)), 5), round(float(np.max(step_ms)), 5)],
@@ -361,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="binned", choices=["binned", "direct"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -47,7 +47,7 @@ EXPORTS = [
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
-    "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats",
+    "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
 ]
 
 
@@ -148,9 +148,14 @@ class Framebuffer:
         _check(self.rast.lib.swrb_fb_get_pixels(self._h, C.c_uint32(layer), _ptr(out), C.c_uint32(out.shape[1])))
         return out
 
-    def get_pixels_device(self, layer: int, device_ptr: int, stride: int | None = None):
-        _check(self.rast.lib.swrb_fb_get_pixels_device(self._h, C.c_uint32(layer), C.c_void_p(device_ptr),
-                                                       C.c_uint32(stride or self.width)))
+    def get_pixels_device(self, layer: int, device_ptr: int, stride: int | None = None, cuda_stream: int | None = None):
+        """GetPixels into device (or NVLink peer) memory; `cuda_stream` launches it on another stream."""
+        if cuda_stream is None:
+            _check(self.rast.lib.swrb_fb_get_pixels_device(self._h, C.c_uint32(layer), C.c_void_p(device_ptr),
+                                                           C.c_uint32(stride or self.width)))
+        else:
+            _check(self.rast.lib.swrb_fb_get_pixels_device_on_stream(self._h, C.c_uint32(layer), C.c_void_p(device_ptr),
+                                                                     C.c_uint32(stride or self.width), C.c_void_p(cuda_stream)))
 
     def destroy(self):
         if self._h:

@@ -204,6 +204,8 @@ static int check_overflow(swrb_device* d) {
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
+static int fb_materialize_for_read(swrb_fb* fb, uint32_t layer);
+
 const char* swrb_last_error(void) { return g_lastError.c_str(); }
 const char* swrb_version(void) { return "swrb 0.1 (sm_100a)"; }
 
@@ -462,7 +464,7 @@ int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host) {
     if (!fb || !dst_host) return fail(SWRB_E_INVALID, "null argument");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
     CU(cudaSetDevice(fb->dev->cudaDevice));
-    int rc = fb_materialize(fb);
+    int rc = fb_materialize_for_read(fb, layer);
     if (rc) return rc;
     CU(cudaMemcpyAsync(dst_host, fb->data + (size_t)layer * fb->layerStride, (size_t)fb->width * fb->height * 4, cudaMemcpyDeviceToHost, fb->dev->stream));
     CU(cudaStreamSynchronize(fb->dev->stream));
@@ -480,20 +482,38 @@ int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host) 
     return SWRB_OK;
 }
 
-int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride) {
+// Layer 0 is already current once the resolve pass has written colour over it, and layers >= 2 never
+// take part in the lazy vis-buffer; only depth / id reads force the key unpack.
+static int fb_materialize_for_read(swrb_fb* fb, uint32_t layer) {
+    if (fb->pendingClear && layer >= 2) return SWRB_OK;
+    if (!fb->pendingClear && fb->visInKeys && (layer >= 2 || (layer == 0 && fb->layer0IsColor))) return SWRB_OK;
+    return fb_materialize(fb);
+}
+
+static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, cudaStream_t stream) {
     if (!fb || !dst_device) return fail(SWRB_E_INVALID, "null argument");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
     if (stride < fb->width || stride % 4) return fail(SWRB_E_INVALID, "stride %u must be >= width and a multiple of 4", stride);
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
-    int rc = fb_materialize(fb);
+    int rc = fb_materialize_for_read(fb, layer);
     if (rc) return rc;
     uint32_t numVec = fb->width * fb->height / 4;
-    k_fb_detile<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
+    k_fb_detile<<<grid_for(d, numVec, 256, 8), 256, 0, stream>>>(
         reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride);
     d->launches++;
     CU(cudaGetLastError());
     return SWRB_OK;
+}
+
+int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    return get_pixels_device_on(fb, layer, dst_device, stride, fb->dev->stream);
+}
+
+int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    return get_pixels_device_on(fb, layer, dst_device, stride, (cudaStream_t)cuda_stream);
 }
 
 int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {

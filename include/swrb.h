@@ -108,6 +108,9 @@ SWRB_API int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_h
 SWRB_API int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host);
 SWRB_API int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride); /* Framebuffer::GetPixels */
 SWRB_API int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride); /* same, device dst */
+/* Same, launched on a caller-provided stream (the caller orders it after the producing call with events);
+ * dst may be peer memory of another GPU: the de-tile kernel then stores straight over NVLink. */
+SWRB_API int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream);
 
 /* ---- hot path ------------------------------------------------------------------------ */
 /* ShadingContext::CullMeshlets frustum part (Shading.cpp:775-809, :865-867). Planes are
