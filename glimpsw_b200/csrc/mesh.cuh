@@ -1,5 +1,5 @@
 // mesh.cuh — K1: meshlet cull-bit/frustum test + mesh shading + clip classification + triangle setup
-// + inline rasterization of small triangles, one warp per meshlet.
+// + rasterization of every triangle that is not "big", one warp per meshlet.
 //
 // Replaces (reference, one worker iteration of Rasterizer::DrawMeshlets, Rasterizer.cpp:535-594):
 //   ShadeMeshlet                 Shading.cpp:281-307   (cull bit, SoA position transform, index copy)
@@ -7,28 +7,29 @@
 //   GatherPos / index widen      Rasterizer.cpp:143-151, :553-558
 //   Clipper::ComputeClipCodes    Rasterizer.cpp:353-397
 //   TrianglePacket::Setup + bbox Rasterizer.cpp:257-289, :331-351
-// and, for triangles whose pixel region is at most kInlineMaxArea pixels, also
+// and, for small and medium triangles, also
 //   TriangleEdgeVars::Setup      Rasterizer.cpp:296-329
 //   DrawTriangle<> + FS_EncodeSurfaceId<false>   Rasterizer.h:250-328, Shading.cpp:309-331
 //
 // Data flow per warp: 6 coalesced 128-byte position loads (lane L owns vertices L and L+32) and 24
 // 128-bit index loads; per-VERTEX perspective divide / snap / outcodes are computed once and parked in
 // shared memory (the CPU recomputes them per triangle corner; same inputs -> same bits); each lane then
-// sets up triangles L, L+32, L+64, L+96 through a shared-memory 64-entry remap.
-//   * Small triangles (the bulk of a meshlet scene) never leave the SM: the lane rasterizes them and
-//     reduces 64-bit depth|id keys straight into the frame's key buffer with REDG.MAX.64 — no triangle
-//     record, no bin entry, no second kernel touches them.
-//   * Larger triangles are appended to a per-warp list in shared memory; after the loop the warp takes
-//     one slice of the global record array (one atomic per meshlet), writes 32-byte records and, on the
-//     binned path, counts them per 32x32-px screen tile (pass 1 of the binner).
+// sets up triangles L, L+32, L+64, L+96 through a shared-memory 64-entry remap. Two size classes:
+//   * small (pixel region <= kInlineMaxArea): the lane that set the triangle up rasterizes it and reduces
+//     64-bit depth|id keys straight into the frame's key buffer with REDG.MAX.64 — no record, no bin
+//     entry, no second kernel. This is the bulk of a meshlet scene.
+//   * big: one slice of the global record array per meshlet (one atomic), 32-byte records, and on the binned
+//     path a per-tile count (pass 1 of the binner); the tile rasterizer stages those in shared memory.
+// (A warp-cooperative middle class was measured and dropped: one warp working through a meshlet's ~100
+// mid-size triangles one after another is a 100+ us serial tail; lanes in parallel or tiles in parallel win.)
 #pragma once
 
 #include "common.cuh"
 
 namespace swrb {
 
-constexpr int kMeshWarps = 8;        // warps (= meshlets in flight) per block
-constexpr int kInlineMaxArea = 32;   // pixel-region size a lane rasterizes itself
+constexpr int kMeshWarps = 8;           // warps (= meshlets in flight) per block
+constexpr int kInlineMaxArea = 256;     // pixel-region size a lane rasterizes itself (else: record + binner)
 
 struct MeshWarpSmem {
     float nx[64], ny[64];       // NDC x, y (for the float determinant)
@@ -36,7 +37,7 @@ struct MeshWarpSmem {
     uint32_t pos[64];           // packed 28.4 x | y << 16
     uint32_t flags[64];         // bits 0-5 Cohen-Sutherland outcodes, bit 6 inside guard band
     uint32_t idx[96];           // Indices[3][128] as bytes
-    uint8_t deferred[128];      // prims that need a record (too large to rasterize inline)
+    uint8_t big[128];           // prims that need a record
 };
 
 __device__ __forceinline__ const DrawItem& find_draw(const DrawItem* draws, uint32_t numDraws, uint32_t work) {
@@ -174,11 +175,11 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
         // ---- triangles: lane owns prims lane + 32k; small ones are rasterized right here
         const uint8_t* idx = reinterpret_cast<const uint8_t*>(s.idx);
         const uint32_t idBase = (d.meshletOffset + meshIdx) * SWR_MAX_PRIMS;
-        uint32_t numDeferred = 0;
+        uint32_t numBig = 0;
 #pragma unroll 1
         for (uint32_t k = 0; k < 4 && k * 32 < primCount; k++) {
             const uint32_t prim = lane + k * 32;
-            bool keep = false, nonTrivial = false, defer = false;
+            bool keep = false, nonTrivial = false, big = false;
             if (prim < primCount) {
                 uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
                 uint32_t f0 = s.flags[i0], f1 = s.flags[i1], f2 = s.flags[i2];
@@ -202,14 +203,15 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     if (keep) {
                         BBox r;
                         if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {     // else: counted, touches no pixel
-                            if (fsId == 0 && (r.maxX - r.minX) * (r.maxY - r.minY) <= kInlineMaxArea) {
+                            const int32_t area = (r.maxX - r.minX) * (r.maxY - r.minY);
+                            if (fsId == 0 && area <= kInlineMaxArea) {
                                 TriRecord t;
                                 t.pos0 = p0; t.pos1 = p1; t.pos2 = p2;
                                 t.z0 = s.z[i0]; t.z1 = s.z[i1]; t.z2 = s.z[i2];
                                 t.id = idBase + prim; t.aux = 0;
                                 raster_inline(t, r, fp, keys);
                             } else {
-                                defer = true;
+                                big = true;
                             }
                         }
                     }
@@ -217,27 +219,28 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             }
             const uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
             const uint32_t clipMask = __ballot_sync(0xFFFFFFFFu, nonTrivial);
-            const uint32_t deferMask = __ballot_sync(0xFFFFFFFFu, defer);
-            if (defer) s.deferred[numDeferred + __popc(deferMask & ((1u << lane) - 1u))] = (uint8_t)prim;
-            numDeferred += __popc(deferMask);
+            const uint32_t bigMask = __ballot_sync(0xFFFFFFFFu, big);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (big) s.big[numBig + __popc(bigMask & lt)] = (uint8_t)prim;
+            numBig += __popc(bigMask);
             if (lane == 0) { nRasterized += __popc(keepMask); nClipped += __popc(clipMask); }   // :579, :568
         }
+        if (numBig) __syncwarp();
 
-        // ---- deferred (larger) triangles: one slice of the record array per meshlet
-        if (numDeferred) {
-            __syncwarp();
+        // ---- big triangles: one slice of the record array per meshlet
+        if (numBig) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->triCount, numDeferred);
+            if (lane == 0) base = atomicAdd(&ctl->triCount, numBig);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            const bool fits = base + numDeferred <= triCapacity;
+            const bool fits = base + numBig <= triCapacity;
             if (!fits && lane == 0) atomicExch(&ctl->overflow, 1u);
-            for (uint32_t j0 = 0; j0 < numDeferred; j0 += 32) {
+            for (uint32_t j0 = 0; j0 < numBig; j0 += 32) {
                 const uint32_t j = j0 + lane;
-                const bool active = fits && j < numDeferred;
+                const bool active = fits && j < numBig;
                 uint32_t tx0 = 1, ty0 = 1, tx1 = 0, ty1 = 0;
                 const uint32_t slot = base + j;
                 if (active) {
-                    const uint32_t prim = s.deferred[j];
+                    const uint32_t prim = s.big[j];
                     uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
                     uint32_t p0 = s.pos[i0], p1 = s.pos[i1], p2 = s.pos[i2];
                     uint4* dst = reinterpret_cast<uint4*>(tris + slot);

@@ -21,12 +21,6 @@ constexpr int kBigBinShift = 7;   // big-triangle work items are 128 x 128 px
 
 struct BigItem { uint32_t tri; uint32_t bin; };   // bin = x | y << 16 in 128-px units
 
-__device__ __forceinline__ void key_max(unsigned long long* keys, uint32_t off, unsigned long long key) {
-    // pre-check through L2 (keys are written by other SMs): skips the atomic for occluded fragments
-    unsigned long long cur = __ldcg(keys + off);
-    if (key > cur) atomicMax(keys + off, key);
-}
-
 __global__ void __launch_bounds__(256)
 k_raster_direct(const TriRecord* __restrict__ tris, FrameParams fp, unsigned long long* __restrict__ keys,
                 BigItem* __restrict__ bigItems, uint32_t bigCapacity, DevCtl* __restrict__ ctl) {
@@ -71,11 +65,6 @@ k_raster_direct(const TriRecord* __restrict__ tris, FrameParams fp, unsigned lon
     }
 }
 
-// Largest value an edge function takes over a w x h pixel block whose top-left pixel has value `v`.
-__device__ __forceinline__ int32_t edge_block_max(int32_t v, int32_t a, int32_t b, int32_t w1, int32_t h1) {
-    return v + (a > 0 ? a * w1 : 0) + (b > 0 ? b * h1 : 0);
-}
-
 __global__ void __launch_bounds__(256)
 k_raster_big(const TriRecord* __restrict__ tris, const BigItem* __restrict__ items, FrameParams fp,
              unsigned long long* __restrict__ keys, DevCtl* __restrict__ ctl) {
@@ -100,38 +89,7 @@ k_raster_big(const TriRecord* __restrict__ tris, const BigItem* __restrict__ ite
         // every block is visited (bit-exact with the reference's wrapped arithmetic).
         const bool mayWrap = !edges_wrap_free(t, e, fp);
 
-        // blocks of 8x4 px aligned to the region origin (rounded down to 8x4)
-        int32_t ox = r.minX & ~7, oy = r.minY & ~3;
-        int32_t blocksX = (r.maxX - ox + 7) >> 3, blocksY = (r.maxY - oy + 3) >> 2;
-        int32_t numBlocks = blocksX * blocksY;
-        for (int32_t base = 0; base < numBlocks; base += 32) {
-            int32_t bi = base + (int32_t)lane;
-            bool alive = bi < numBlocks;
-            int32_t bxp = ox + (bi % blocksX) * 8, byp = oy + (bi / blocksX) * 4;
-            if (alive && !mayWrap) {
-                int32_t v0 = e.e0 + e.a12 * bxp + e.b12 * byp;
-                int32_t v1 = e.e1 + e.a20 * bxp + e.b20 * byp;
-                int32_t v2 = e.e2 + e.a01 * bxp + e.b01 * byp;
-                alive = (edge_block_max(v0, e.a12, e.b12, 7, 3) | edge_block_max(v1, e.a20, e.b20, 7, 3) |
-                         edge_block_max(v2, e.a01, e.b01, 7, 3)) >= 0;
-            }
-            uint32_t todo = __ballot_sync(0xFFFFFFFFu, alive);
-            while (todo) {
-                int32_t src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                int32_t px = __shfl_sync(0xFFFFFFFFu, bxp, src) + (int32_t)(lane & 7u);
-                int32_t py = __shfl_sync(0xFFFFFFFFu, byp, src) + (int32_t)(lane >> 3);
-                if (px >= r.minX && px < r.maxX && py >= r.minY && py < r.maxY) {
-                    uint32_t e0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)px + (uint32_t)e.b12 * (uint32_t)py;
-                    uint32_t e1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)px + (uint32_t)e.b20 * (uint32_t)py;
-                    uint32_t e2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)px + (uint32_t)e.b01 * (uint32_t)py;
-                    if ((int32_t)(e0 | e1 | e2) >= 0) {
-                        float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);
-                        if (d > 0.0f) key_max(keys, fb_pixel_offset((uint32_t)px, (uint32_t)py, fp.width), make_key(d, t.id));
-                    }
-                }
-            }
-        }
+        warp_raster_region<true>(t, e, r, mayWrap, fp, keys);
     }
 }
 

@@ -750,7 +750,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     // record consumers are grid-stride loops over a device-side count; size their grids from the last count
     // the host has seen (any grid is correct, a fitting one avoids launching a thousand idle blocks)
     const uint64_t recEstimate = std::min<uint64_t>(d->triCap, std::max<uint64_t>(4096, 4 * (uint64_t)d->lastTriCount));
-    const uint32_t scatterGrid = grid_for(d, recEstimate, 256, 8);
+    const uint32_t scatterGrid = std::max<uint32_t>(grid_for(d, recEstimate, 256, 8), (uint32_t)d->numSMs);
     if (binned) {
         {
             StageScope ss(d, SWRB_STAGE_MESH);
