@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kMeshWarps * 32, 3)
 k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
              const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
              unsigned long long* __restrict__ keys,
-             TriRecord* __restrict__ tris, TriRecordW* __restrict__ trisW, uint32_t triCapacity,
+             TriRecord* __restrict__ tris, TriRecord* __restrict__ alphaTris, TriRecordW* __restrict__ alphaW, uint32_t triCapacity,
              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, DevCtl* __restrict__ ctl) {
     __shared__ MeshWarpSmem smem[kMeshWarps];
     MeshWarpSmem& s = smem[threadIdx.x >> 5];
@@ -228,7 +228,23 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
         if (numBig) __syncwarp();
 
         // ---- big triangles: one slice of the record array per meshlet
-        if (numBig) {
+        if (numBig && fsId) {
+            // alpha-tested meshlet (FragmentShaderId 1): every surviving triangle goes to the alpha list with the
+            // 1/w of its vertices; k_raster_alpha runs the textured fragment program on them
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->alphaCount, numBig);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const bool fits = base + numBig <= triCapacity && alphaTris != nullptr;
+            if (!fits && lane == 0) atomicExch(&ctl->overflow, 1u);
+            for (uint32_t j = lane; fits && j < numBig; j += 32) {
+                const uint32_t prim = s.big[j];
+                uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
+                uint4* dst = reinterpret_cast<uint4*>(alphaTris + base + j);
+                dst[0] = make_uint4(s.pos[i0], s.pos[i1], s.pos[i2], __float_as_uint(s.z[i0]));
+                dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), idBase + prim, 1u);
+                *reinterpret_cast<float4*>(alphaW + base + j) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], 0.0f);
+            }
+        } else if (numBig) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&ctl->triCount, numBig);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -245,8 +261,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     uint32_t p0 = s.pos[i0], p1 = s.pos[i1], p2 = s.pos[i2];
                     uint4* dst = reinterpret_cast<uint4*>(tris + slot);
                     dst[0] = make_uint4(p0, p1, p2, __float_as_uint(s.z[i0]));
-                    dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), idBase + prim, fsId);
-                    if (fsId) *reinterpret_cast<float4*>(trisW + slot) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], 0.0f);
+                    dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), idBase + prim, 0u);
                     if (kBinned) {
                         BBox r;
                         raster_region(p0, p1, p2, fp.halfW, fp.halfH, r);

@@ -24,6 +24,7 @@
 #include "raster_direct.cuh"
 #include "fbops.cuh"
 #include "resolve.cuh"
+#include "alpha.cuh"
 
 using namespace swrb;
 
@@ -63,7 +64,8 @@ struct swrb_device {
     DevCtl* ctlHost = nullptr;        // pinned mirror
 
     TriRecord* tris = nullptr;
-    TriRecordW* trisW = nullptr;
+    TriRecord* alphaTris = nullptr;   // alpha-tested triangles (only allocated for scenes with AlphaCutoff < 255 materials)
+    TriRecordW* trisW = nullptr;      // their 1/w
     uint32_t* bigList = nullptr;      // binned: big triangle indices (capacity triCap)
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
@@ -236,7 +238,7 @@ void swrb_device_destroy(swrb_device* d) {
     if (!d) return;
     cudaSetDevice(d->cudaDevice);
     cudaStreamSynchronize(d->stream);
-    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->bigList);
+    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->alphaTris); cudaFree(d->bigList);
     cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
@@ -615,9 +617,13 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
         if (d->bigList) { CU(cudaFree(d->bigList)); d->bigList = nullptr; }
         CU(cudaMalloc(&d->bigList, needTris * 4));
         if (d->trisW) { CU(cudaFree(d->trisW)); d->trisW = nullptr; }
+        if (d->alphaTris) { CU(cudaFree(d->alphaTris)); d->alphaTris = nullptr; }
         d->triCap = needTris;
     }
-    if (alphaTest && !d->trisW) CU(cudaMalloc(&d->trisW, d->triCap * sizeof(TriRecordW)));
+    if (alphaTest && !d->trisW) {      // alpha-tested triangles have their own record list (+ 1/w per vertex)
+        CU(cudaMalloc(&d->trisW, d->triCap * sizeof(TriRecordW)));
+        CU(cudaMalloc(&d->alphaTris, d->triCap * sizeof(TriRecord)));
+    }
     uint64_t needBins = std::max<uint64_t>(d->reserveBins, 2 * d->triCap + (1u << 20));
     if (needBins > d->binCap) {
         int rc = ensure_buffer((void**)&d->binEntries, &d->binCap, needBins, 4);
@@ -657,7 +663,7 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
 }
 
 static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
-                         bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws) {
+                         const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws) {
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     if (numDraws == 0) return SWRB_OK;
@@ -755,7 +761,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                           d->tris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, d->ctl);
+                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, d->ctl);
             d->launches++;
         }
         {
@@ -775,7 +781,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                            d->tris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr, d->ctl);
+                                                                            d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr, d->ctl);
             d->launches++;
         }
         {
@@ -784,6 +790,11 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
             k_raster_big<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
             d->launches += 2;
         }
+    }
+    if (alphaTest && texturesDev != nullptr) {     // FS_EncodeSurfaceId<true> for the alpha list (both raster modes)
+        StageScope ss(d, SWRB_STAGE_RASTER);
+        k_raster_alpha<<<d->numSMs * 4, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, fb->keys, d->ctl);
+        d->launches++;
     }
     // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the
     // resolve pass reads the keys directly. If a work list overflowed, the draw was aborted on the device
@@ -802,7 +813,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
 int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws) {
     if (!fb || !scene || (!draws && num_draws)) return fail(SWRB_E_INVALID, "null argument");
     if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
-    return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->hasAlphaTest, draws, num_draws);
+    return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, draws, num_draws);
 }
 
 int swrb_draw_meshlets(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draw) {
@@ -827,7 +838,7 @@ int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint3
     desc.MeshletCount = count;
     memcpy(desc.ObjectToClip, object_to_clip, sizeof(desc.ObjectToClip));
     desc.CullBitmapHost = cull_bitmap_host;
-    return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, false, &desc, 1);
+    return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, nullptr, false, &desc, 1);
 }
 
 // ---- resolve -----------------------------------------------------------------------------------

@@ -204,6 +204,82 @@ inline void draw_triangle(uint32_t* color, float* depth, uint32_t width, const T
 
 }  // namespace
 
+// Texture2D::SampleImplicitLod<SurfaceSampler> over one 4x4 fragment (oracle_resolve.cpp).
+extern "C" void orc_sample_implicit_lod_4x4(const swr_texture_desc* tex, const float* u, const float* v, uint32_t* out);
+
+namespace {
+
+inline float half_to_float(uint16_t h) {   // _mm_cvtph_ps (exact)
+    uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 31, man = h & 1023;
+    if (exp == 0) {
+        if (man == 0) return u2f(sign);
+        return u2f(f2u((float)man * (1.0f / 16777216.0f)) | sign);
+    }
+    if (exp == 31) return u2f(sign | 0x7F800000u | (man << 13));
+    return u2f(sign | ((exp + 112) << 23) | (man << 13));
+}
+
+// Rasterizer::DrawTriangle<FS_EncodeSurfaceId<true>, false> — Rasterizer.h:250-328 + Shading.cpp:309-331.
+// Per 4x4 fragment like the reference, because the texture LOD comes from finite differences over all 16
+// lanes of the fragment (Texture.h:260-269, :403-410) and the filter choice is a fragment-wide vote (:432).
+// Canonical arithmetic for the perspective correction: approx_rcp -> 1/w, then the source's Newton step.
+inline void draw_triangle_alpha(uint32_t* color, float* depth, uint32_t width, const TriEdges& e,
+                                uint32_t bbMin, uint32_t bbMax, uint32_t surfaceId, const uint32_t packedTC[3],
+                                const swr_texture_desc* tex, uint32_t alphaCutoff) {
+    uint32_t minX = bbMin & 0xFFFF, minY = bbMin >> 16, maxX = bbMax & 0xFFFF, maxY = bbMax >> 16;
+    float uv[3][2];
+    for (int k = 0; k < 3; k++) {                                                     // UnpackHalf2x16 (Shading.cpp:227-230)
+        uv[k][0] = half_to_float((uint16_t)(packedTC[k] & 0xFFFF));
+        uv[k][1] = half_to_float((uint16_t)(packedTC[k] >> 16));
+    }
+    for (uint32_t y0 = minY; y0 < maxY; y0 += 4) {
+        for (uint32_t x0 = minX; x0 < maxX; x0 += 4) {
+            bool mask[16];
+            bool any = false;
+            float d[16], tu[16], tv[16];
+            uint32_t off0 = ((x0 & ~3u) << 2) + (y0 & ~3u) * width;
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = x0 + (i & 3), y = y0 + (i >> 2);
+                uint32_t e0 = (uint32_t)e.Edge0 + (uint32_t)e.A12 * x + (uint32_t)e.B12 * y;
+                uint32_t e1 = (uint32_t)e.Edge1 + (uint32_t)e.A20 * x + (uint32_t)e.B20 * y;
+                uint32_t e2 = (uint32_t)e.Edge2 + (uint32_t)e.A01 * x + (uint32_t)e.B01 * y;
+                mask[i] = (int32_t)(e0 | e1 | e2) >= 0;                                // Rasterizer.h:289-290
+                float u = (float)(int32_t)e1, v = (float)(int32_t)e2;
+                d[i] = std::fmaf(u, e.Z10, std::fmaf(v, e.Z20, e.Z0));                 // :296
+                // perspective correction (:302-310, :319)
+                float pw0 = std::fmaf(u + v, -e.W0S, e.W0);
+                float w = std::fmaf(u, e.W1S, std::fmaf(v, e.W2S, pw0));
+                float rcpW = 1.0f / w;
+                rcpW *= std::fmaf(-w, rcpW, 2.0f);
+                u *= e.W1S * rcpW;
+                v *= e.W2S * rcpW;
+                float b0 = 1 - u - v;
+                // vars.Interpolate = BaryLerp (Rasterizer.h:101-104), v0,v1,v2 = VertexId[0..2]
+                tu[i] = std::fmaf(uv[0][0], b0, std::fmaf(uv[1][0], u, uv[2][0] * v));
+                tv[i] = std::fmaf(uv[0][1], b0, std::fmaf(uv[1][1], u, uv[2][1] * v));
+                any = any || mask[i];
+            }
+            if (!any) continue;                                                        // Rasterizer.h:292
+            any = false;
+            for (int i = 0; i < 16; i++) {                                             // Shading.cpp:311-313
+                mask[i] = mask[i] && (d[i] > depth[off0 + i]);
+                any = any || mask[i];
+            }
+            if (!any) continue;
+            uint32_t texel[16];
+            orc_sample_implicit_lod_4x4(tex, tu, tv, texel);                           // :324
+            for (int i = 0; i < 16; i++) {
+                if (mask[i] && texel[i] >= (alphaCutoff << 24)) {                      // :326
+                    depth[off0 + i] = d[i];
+                    color[off0 + i] = surfaceId;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 // ShadeMeshlet — Shading.cpp:281-307. cullBitmap may be NULL. `index` is the meshlet index
@@ -265,12 +341,28 @@ int orc_probe_triangle(const float* v, uint32_t width, uint32_t height, int cull
 //   meshlets    : scene base pointer; the draw covers [meshletOffset, meshletOffset+count)
 //   flags bit0  : guard band enabled (the binned path always enables it, Rasterizer.cpp:509)
 //   counters[4] : TrianglesProcessed, TrianglesRasterized, TrianglesClipped, (unused) — accumulated
-// Alpha-tested materials (FragmentShaderId 1) are drawn with the opaque program here; the alpha
-// variant lives in oracle_resolve.cpp because it needs the texture sampler.
+// `textures` == NULL: alpha-tested materials (FragmentShaderId 1) are drawn with the opaque program.
+// Otherwise they run FS_EncodeSurfaceId<true> (draw_triangle_alpha above); the sampler itself lives in
+// oracle_resolve.cpp (orc_sample_implicit_lod_4x4).
+void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_t height,
+                          const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                          const float* objectToClip, const uint16_t* cullBitmap,
+                          const swr_material* materials, const swr_texture_desc* textures,
+                          uint32_t flags, uint64_t* counters);
+
 void orc_draw_meshlets(uint32_t* color, float* depth, uint32_t width, uint32_t height,
                        const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
                        const float* objectToClip, const uint16_t* cullBitmap,
                        const swr_material* materials, uint32_t flags, uint64_t* counters) {
+    orc_draw_meshlets_ex(color, depth, width, height, meshlets, meshletOffset, count, objectToClip, cullBitmap, materials,
+                         nullptr, flags, counters);
+}
+
+void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_t height,
+                          const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                          const float* objectToClip, const uint16_t* cullBitmap,
+                          const swr_material* materials, const swr_texture_desc* textures,
+                          uint32_t flags, uint64_t* counters) {
     int halfW = (int)width / 2, halfH = (int)height / 2;                                   // :508
     float bx = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)width : 1.0f;             // :509
     float by = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)height : 1.0f;
@@ -298,7 +390,15 @@ void orc_draw_meshlets(uint32_t* color, float* depth, uint32_t width, uint32_t h
             TriEdges e;
             edge_setup(t, halfW, halfH, e);                                                // :721
             uint32_t surfaceId = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;         // Shading.cpp:328
-            draw_triangle(color, depth, width, e, bbMin, bbMax, surfaceId);
+            if (mesh.FragmentShaderId == 1 && textures != nullptr) {                       // Rasterizer.cpp:729 (DrawTriangle[FragmentShaderId])
+                const swr_meshlet& src = meshlets[meshletOffset + meshIdx];
+                const swr_material& mat = materials[src.MaterialId];
+                uint32_t tc[3] = { src.TexCoords[mesh.Indices[0][prim] & 63], src.TexCoords[mesh.Indices[1][prim] & 63],
+                                   src.TexCoords[mesh.Indices[2][prim] & 63] };
+                draw_triangle_alpha(color, depth, width, e, bbMin, bbMax, surfaceId, tc, &textures[mat.TextureId], mat.AlphaCutoff);
+            } else {
+                draw_triangle(color, depth, width, e, bbMin, bbMax, surfaceId);
+            }
         }
     }
 }

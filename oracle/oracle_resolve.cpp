@@ -441,6 +441,28 @@ void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t h
                      objectToWorld3, invScreenProj, viewPos, exposure, 0, height);
 }
 
+// Texture2D::SampleImplicitLod<SurfaceSampler>(u, v, layer 0) over one 4x4 fragment (Texture.h:403-410):
+// LOD from 2x2 finite differences inside the fragment (dFdx/dFdy, :260-269), CalcMipLevel(grad) - LerpFracBits
+// (:271-275, :408), fragment-wide filter vote in SampleLevel (:432). Used by the alpha-tested fragment program.
+void orc_sample_implicit_lod_4x4(const swr_texture_desc* tex, const float* u, const float* v, uint32_t* out) {
+    const float scaleLerpU = (float)(tex->Width << 8), scaleLerpV = (float)(tex->Height << 8);
+    float su[N], sv[N];
+    for (int i = 0; i < N; i++) { su[i] = u[i] * scaleLerpU; sv[i] = v[i] * scaleLerpV; }
+    int32_t mip[N];
+    bool anyMin = false;
+    for (int i = 0; i < N; i++) {
+        int row = i >> 2, x = i & 3;
+        int ax = row * 4 + (x & ~1), bx = row * 4 + (x | 1);          // dFdx: [1 1 3 3] - [0 0 2 2] within a row
+        int ay = (row & ~1) * 4 + x, by = (row | 1) * 4 + x;          // dFdy: rows [1 1 3 3] - rows [0 0 2 2]
+        float g[4] = { su[bx] - su[ax], sv[bx] - sv[ax], su[by] - su[ay], sv[by] - sv[ay] };
+        float dx = std::fmaf(g[0], g[0], g[1] * g[1]);
+        float dy = std::fmaf(g[2], g[2], g[3] * g[3]);
+        mip[i] = (ilog2(std::fmax(dx, dy)) >> 1) - 8;
+        anyMin = anyMin || mip[i] > 0;
+    }
+    for (int i = 0; i < N; i++) out[i] = sample_level(*tex, u[i], v[i], 0, mip[i], anyMin);
+}
+
 // Texture2D::GenerateMip for one layer/level (Texture.h:577-596): 2x2 box filter in float, RNE pack.
 void orc_generate_mip(uint32_t* data, const swr_texture_desc* t, uint32_t layer, uint32_t level) {
     uint32_t w = t->Width >> level, h = t->Height >> level;

@@ -61,16 +61,21 @@ class Framebuffer:
 
 
 def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, count: int, object_to_clip,
-                  cull_bitmap=None, materials=None, guardband: bool = True, counters=None) -> np.ndarray:
-    """Rasterizer::DrawMeshlets + VisBufferShader on the CPU. Returns the 4 integer perf counters."""
+                  cull_bitmap=None, materials=None, guardband: bool = True, counters=None, textures=None) -> np.ndarray:
+    """Rasterizer::DrawMeshlets + VisBufferShader on the CPU. Returns the 4 integer perf counters.
+
+    With `textures`, alpha-tested materials (AlphaCutoff < 255) run FS_EncodeSurfaceId<true>; without, every
+    triangle takes the opaque program."""
+    assert meshlets.dtype.itemsize == 1728
     if counters is None:
         counters = np.zeros(4, dtype=np.uint64)
     m = _mat(object_to_clip)
     cb = None if cull_bitmap is None else _p(np.ascontiguousarray(cull_bitmap, dtype=np.uint16))
     mats = None if materials is None or len(materials) == 0 else _p(materials)
-    lib().orc_draw_meshlets(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
-                            C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats,
-                            C.c_uint32(1 if guardband else 0), _p(counters))
+    descs, keep = (None, None) if not textures else _texture_descs(textures)
+    lib().orc_draw_meshlets_ex(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
+                               C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats, descs,
+                               C.c_uint32(1 if guardband else 0), _p(counters))
     return counters
 
 

@@ -15,7 +15,8 @@ def oracle_render(orc, scene, cull=False, clear=(0xFF000000, 0.0), fb=None):
             planes = orc.frustum_planes(proj, view, node.model)
             bitmap, _ = orc.cull_meshlets(scene.meshlets[node.meshlet_offset:node.meshlet_offset + node.meshlet_count], planes)
         orc.draw_meshlets(fb, scene.meshlets, node.meshlet_offset, node.meshlet_count, scene.object_to_clip(node),
-                          cull_bitmap=bitmap, materials=scene.materials, counters=counters)
+                          cull_bitmap=bitmap, materials=scene.materials, counters=counters,
+                          textures=scene.textures if len(scene.textures) else None)
     return fb, counters
 
 
