@@ -30,3 +30,33 @@ def test_config2_grid_1m_1080p(orc, rast_factory, binning):
     assert [gc["TrianglesProcessed"], gc["TrianglesRasterized"], gc["TrianglesClipped"]] == [int(oc[0]), int(oc[1]), int(oc[2])]
     # GetPixels de-tiling agrees with the oracle's
     assert np.array_equal(gfb.get_pixels(0), ofb.get_pixels(0))
+
+
+def test_config4_instanced_10m_culled_1080p(orc, rast_factory):
+    """BASELINE config C4: ~10 M-triangle instanced scene (122 draws), frustum cull bitmap per node, 1920x1080."""
+    scene = scenes.instanced_scene()
+    assert scene.num_triangles > 9_900_000
+    ofb, oc = oracle_render(orc, scene, cull=True)
+    assert int(oc[0]) < 0.4 * scene.num_triangles            # heavy culling: >= 60 % of the triangles never reach setup
+    for binning in (True, False):
+        gfb, gc, _ = gpu_render(rast_factory(enable_binning=binning), scene, cull=True)
+        assert_visbuffer_equal(ofb, gfb, f"C4 binning={binning}")
+        assert [gc["TrianglesProcessed"], gc["TrianglesRasterized"], gc["TrianglesClipped"]] == [int(oc[0]), int(oc[1]), int(oc[2])]
+
+
+def test_config3_textured_alpha_1440p(orc, rast_factory):
+    """BASELINE config C3 stand-in: ~260 K textured triangles incl. a double-sided alpha-masked material, 2560x1440."""
+    scene = scenes.torus_knot_scene(600, 216, 2560, 1440, tex_size=512, alpha_material=True)
+    assert scene.num_triangles == 259200
+    ofb, oc = oracle_render(orc, scene)
+    gfb, gc, _ = gpu_render(rast_factory(), scene)
+    assert_visbuffer_equal(ofb, gfb, "C3")
+    assert gc["TrianglesRasterized"] == int(oc[1])
+
+
+def test_max_render_size_2896(orc, rast_factory):
+    """The reference's fixed-point limit (Rasterizer.h:203): 2896 x 2896."""
+    scene = scenes.grid_scene(40, 40, 2896, 2896, seed=12)
+    ofb, oc = oracle_render(orc, scene)
+    gfb, gc, _ = gpu_render(rast_factory(), scene)
+    assert_visbuffer_equal(ofb, gfb, "2896^2")
