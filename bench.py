@@ -5,17 +5,27 @@ A "step" is one frame of the hot path over one batch of synthetic input: Framebu
 Rasterizer::DrawMeshlets (vis-buffer) -> ShadingContext::Resolve, i.e. BASELINE.json's metric
 "Mtri/s and frames/s @1080p vis-buffer+resolve". Workload at N=1: BASELINE config C2 geometry
 (procedural 999,600-triangle meshlet grid, 1920x1080) bound to a procedural two-layer material so the
-resolve pass samples textures. `value` = scene triangles submitted per second with the scene resident
-in HBM; `e2e` = the same frame through the C ABI with HOST buffers (meshlets uploaded from pinned
-memory and the resolved image read back every step).
+resolve pass samples textures.
+
+  value   whole-job throughput, scene resident in HBM: K frames submitted round-robin to F (default 3)
+          independent render contexts (own stream, framebuffer, work buffers) so that the issue-bound resolve
+          of one frame overlaps the latency-bound mesh/raster kernels of the next. Inputs are larger than L2:
+          the contexts rotate over 8 copies of the 17.6 MB meshlet buffer (141 MB > 126 MB L2), so no frame
+          finds its meshlets cached. Timed with CUDA events on the launching streams; max over ranks.
+  latency the same frame strictly serialised on one stream with the L2 evicted before every step
+          (`latency_ms_per_frame`, `stages`, `roofline` come from this mode).
+  e2e     the same metric through the C ABI with HOST buffers: every step uploads the meshlets from pinned
+          host memory (H2D), renders, and reads the resolved image back (D2H); the F contexts keep the copies
+          and the kernels of different steps overlapped.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode binned|direct]
 
-N>1 (torchrun, one rank per GPU): views are independent units, so every rank renders its own camera of
-the same scene (weak scaling, no data-path collective); the resolved 1080p composites are gathered to
-rank 0 with NCCL inside the timed region (BASELINE config C5's composite gather).
---impl reference: the CPU restatement of the reference (oracle/baseline_mt.cpp, all host threads) runs
-the same frames on rank 0; the upstream binary cannot be built in this image.
+N>1 (torchrun, one rank per GPU): views are independent units, so every rank renders its own camera of the
+same scene (weak scaling, no data-path collective); the resolved 1080p composites are collected on rank 0:
+each rank's de-tile kernel stores straight into rank 0's memory over NVLink (--gather p2p, default) or NCCL
+gather (--gather nccl), on a side stream, double-buffered; the tail is inside the timed region.
+--impl reference: the CPU restatement of the reference (oracle/baseline_mt.cpp, all host threads) runs the same
+frames on rank 0; the upstream binary cannot be built in this image.
 """
 from __future__ import annotations
 
@@ -26,6 +36,7 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -37,6 +48,8 @@ from glimpsw_b200.layout import MATERIAL_DTYPE  # noqa: E402
 
 METRIC = "Mtri/s @1080p vis-buffer+resolve"
 UNIT = "Mtri/s"
+SCENE_COPIES = 8          # x 17.6 MB of meshlets = 141 MB > 126 MB L2
+SLOTS = 4                 # N > 1: composite buffers in flight per rank
 
 
 def build_workload(rank: int = 0):
@@ -65,10 +78,11 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            time.sleep(0.12)          # let the first sample land before the (short) timed region starts
         except Exception:
             self.proc = None
 
@@ -79,7 +93,7 @@ class ClockSampler:
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
@@ -94,7 +108,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(scene, counters):
+def algorithmic_bytes(scene):
     """compulsory DRAM bytes per frame of each stage."""
     m_tested = len(scene.meshlets)
     m_visible = m_tested          # C2: every meshlet is inside the frustum, no cull bitmap
@@ -105,7 +119,7 @@ def algorithmic_bytes(scene, counters):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from glimpsw_b200 import api
+    from glimpsw_b200 import api, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,31 +133,35 @@ def run_ours(args):
     scene = build_workload(rank)
     node = scene.nodes[0]
     tris = scene.num_triangles
-    rast = api.Rasterizer(local_rank, enable_binning=(args.mode == "binned"))
-    # One in-order, non-default stream for our kernels, the torch timing events and NCCL. (torch's default
-    # stream has handle 0, which swrb_device_set_stream reads as "use your own stream": events recorded
-    # there would not be ordered with the kernels.)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    rast.set_stream(stream.cuda_stream)
-    gscene = rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)
-    fb = rast.create_framebuffer(scene.width, scene.height)
-    batch = rast.make_batch([dict(offset=node.meshlet_offset, count=node.meshlet_count, object_to_clip=scene.object_to_clip(node))])
     uni = scenes.resolve_uniforms(scene, node)
-    # N > 1: the resolved composite of every view is gathered to rank 0 over NVLink. Default: the de-tile
-    # kernel of each rank stores straight into rank 0's buffer (peer memory, glimpsw_b200.sharding.PeerComposites)
-    # with device-side ready/ack signals; fallback (--gather nccl): NCCL gather on a side stream. Either way
-    # the exchange of frame k overlaps the render of frame k+1 (double-buffered) and the tail is timed.
-    from glimpsw_b200 import sharding
+    uni_c = api.Rasterizer.make_uniforms(**uni)       # the C uniform block, built once
+    F = max(1, args.in_flight)
+    copies = (SCENE_COPIES + F - 1) // F
+
+    # ---- F independent render contexts on this GPU. Streams are explicit non-default torch streams (torch's
+    # default stream has handle 0, which swrb_device_set_stream reads as "use your own stream").
+    ctxs = []
+    for i in range(F):
+        r = api.Rasterizer(local_rank, enable_binning=(args.mode == "binned"))
+        st = torch.cuda.Stream()
+        assert st.cuda_stream != 0
+        r.set_stream(st.cuda_stream)
+        c = SimpleNamespace(rast=r, stream=st, fb=r.create_framebuffer(scene.width, scene.height),
+                            scenes=[r.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights) for _ in range(copies)],
+                            batch=r.make_batch([dict(offset=node.meshlet_offset, count=node.meshlet_count,
+                                                     object_to_clip=scene.object_to_clip(node))]),
+                            uses=0, resolved=torch.cuda.Event(), copied=None)
+        ctxs.append(c)
+
+    # ---- N > 1: composites go to rank 0 over NVLink, on a side stream, double-buffered
     comm = torch.cuda.Stream() if world > 1 else None
-    gather_kind = "none"
-    peers = None
+    gather_kind, peers = "none", None
     if world > 1:
         gather_kind = args.gather
         if gather_kind == "p2p":
             try:
-                peers = sharding.PeerComposites(scene.height, scene.width, rank, world)
+                with torch.cuda.stream(comm):
+                    peers = sharding.PeerComposites(scene.height, scene.width, rank, world, slots=SLOTS)
             except Exception as exc:          # symmetric memory unavailable: use the collective
                 if rank == 0:
                     print(f"bench.py: peer-memory gather unavailable ({exc!r}); using NCCL gather", file=sys.stderr)
@@ -152,71 +170,92 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks must agree
         if int(flag.item()) == 0 and gather_kind == "p2p":
             gather_kind, peers = "nccl", None
-    composites = [torch.empty((scene.height, scene.width), dtype=torch.int32, device="cuda") for _ in range(2)]
-    gathered = [[torch.empty_like(composites[0]) for _ in range(world)] for _ in range(2)] if (gather_kind == "nccl" and rank == 0) else [None, None]
-    rendered = [torch.cuda.Event() for _ in range(2)]
-    gather_done = [torch.cuda.Event() for _ in range(2)]
+    exchange = world > 1 and gather_kind != "none"
+    composites = [torch.empty((scene.height, scene.width), dtype=torch.int32, device="cuda") for _ in range(SLOTS)]
+    gathered = [[torch.empty_like(composites[0]) for _ in range(world)] for _ in range(SLOTS)] if (gather_kind == "nccl" and rank == 0) else [None] * SLOTS
+    gather_done = [torch.cuda.Event() for _ in range(SLOTS)]
+    coll = torch.cuda.Stream() if world > 1 else None      # rank 0 waits for its peers here, not on the stream that sends its own view
     state = {"k": 0}
 
-    resolved = torch.cuda.Event()
-
-    def frame():
-        fb.clear(0xFF000000, 0.0)
-        rast.draw_prebuilt(fb, gscene, batch)
-        exchange = world > 1 and gather_kind != "none"
-        if exchange and state["k"] > 0:
-            stream.wait_event(gather_done[(state["k"] - 1) & 1])     # the previous frame's de-tile has read layer 0
-        rast.resolve(fb, gscene, **uni)
+    def frame(c, gscene):
+        """Framebuffer::Clear -> DrawMeshlets -> Resolve on context c (+ the composite exchange when N > 1)."""
+        c.fb.clear(0xFF000000, 0.0)
+        c.rast.draw_prebuilt(c.fb, gscene, c.batch)
+        if exchange and c.copied is not None:
+            c.stream.wait_event(c.copied)                       # the previous de-tile of this context has read layer 0
+        c.rast.resolve_prebuilt(c.fb, gscene, uni_c)
         if exchange:
-            slot = state["k"] & 1
+            slot = state["k"] % SLOTS
             state["k"] += 1
-            resolved.record(stream)
-            with torch.cuda.stream(comm):                            # everything below runs beside the next frame's draw
-                comm.wait_event(resolved)
+            c.resolved.record(c.stream)
+            with torch.cuda.stream(comm):                       # beside the next frames' kernels
+                comm.wait_event(c.resolved)
                 if peers is not None:
-                    peers.before_write(slot, comm)
-                    fb.get_pixels_device(0, peers.dst_ptr(slot), cuda_stream=comm.cuda_stream)   # GetPixels straight into rank 0's memory
-                    peers.after_write(slot, comm)
-                    peers.collect(slot, comm)
+                    dbg = os.environ.get("SWRB_BENCH_P2P_DEBUG", "")       # diagnostic switches: "nosignal", "nocopy"
+                    if "nosignal" not in dbg:
+                        peers.before_write(slot, comm)
+                    if "nocopy" in dbg:
+                        pass
+                    elif "ce" in dbg:      # de-tile locally, then a copy-engine transfer into rank 0's memory
+                        c.fb.get_pixels_device(0, composites[slot].data_ptr(), cuda_stream=comm.cuda_stream)
+                        peers.root[slot, rank].copy_(composites[slot], non_blocking=True)
+                    else:
+                        c.fb.get_pixels_device(0, peers.dst_ptr(slot), cuda_stream=comm.cuda_stream)   # GetPixels straight into rank 0's memory
+                    if c.copied is None:
+                        c.copied = torch.cuda.Event()           # per context: a shared per-slot event would be re-recorded by
+                    c.copied.record(comm)                       # later frames and chain consecutive frames together
+                    if "nosignal" not in dbg:
+                        peers.after_write(slot, comm)
+                        peers.collect(slot, coll)               # rank 0 waits for its peers on a third stream
+                    gather_done[slot].record(coll if rank == 0 else comm)
                 else:
-                    fb.get_pixels_device(0, composites[slot].data_ptr(), cuda_stream=comm.cuda_stream)
+                    comm.wait_event(gather_done[slot])
+                    c.fb.get_pixels_device(0, composites[slot].data_ptr(), cuda_stream=comm.cuda_stream)
+                    if c.copied is None:
+                        c.copied = torch.cuda.Event()
+                    c.copied.record(comm)
                     dist.gather(composites[slot], gathered[slot], dst=0)
-                gather_done[slot].record(comm)
+                    gather_done[slot].record(comm)
+
+    def frame_rr(k):
+        c = ctxs[k % F]
+        frame(c, c.scenes[(k // F) % copies])
 
     def barrier():
-        if world > 1:
-            comm.synchronize()
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        frame()
+    for k in range(max(args.warmup, 3) * F):
+        frame_rr(k)
     barrier()
 
-    # ---- timed region: exactly K steps; L2 is flushed before each step, outside the step's events
+    # ---- timed region (throughput): exactly K frames, F in flight, inputs larger than L2
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = rast.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    launches0 = sum(c.rast.launch_count() for c in ctxs)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
-    for b, e in ev:
-        rast.flush_l2()
-        b.record(stream)
-        frame()
-        e.record(stream)
-    tail[0].record(stream)
-    if world > 1:                                                 # the last gathers are part of the job
-        stream.wait_event(gather_done[0])
-        stream.wait_event(gather_done[1])
-    tail[1].record(stream)
+    t0.record(ctxs[0].stream)
+    for c in ctxs[1:]:
+        c.stream.wait_event(t0)
+    for k in range(args.steps):
+        frame_rr(k)
+    for c in ctxs[1:]:
+        ev = torch.cuda.Event()
+        ev.record(c.stream)
+        ctxs[0].stream.wait_event(ev)
+    if exchange:                                                  # the last exchanges are part of the job
+        for ev_done in gather_done:
+            ctxs[0].stream.wait_event(ev_done)
+    t1.record(ctxs[0].stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = rast.launch_count() - launches0
+    launches = sum(c.rast.launch_count() for c in ctxs) - launches0
     clocks = sampler.stop()
-    step_ms = [b.elapsed_time(e) for b, e in ev]
-    total_ms = float(sum(step_ms)) + tail[0].elapsed_time(tail[1])
+    total_ms = t0.elapsed_time(t1)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -224,21 +263,36 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = tris * world / (ms_per_step * 1e-3) / 1e6
 
-    # ---- per-stage device times (events around every kernel group, one extra frame) for the roofline
+    # ---- latency mode: one context, strictly serial, L2 evicted before every frame; per-stage times for the roofline
+    c0 = ctxs[0]
+    rast = c0.rast
+    lat_steps = min(args.steps, 100)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(lat_steps)]
+    save_exchange, exchange = exchange, False
+    for b, e in ev:
+        rast.flush_l2()
+        b.record(c0.stream)
+        frame(c0, c0.scenes[0])
+        e.record(c0.stream)
+    torch.cuda.synchronize()
+    lat_ms = [b.elapsed_time(e) for b, e in ev]
     rast.enable_stage_timing(True)
     stage_acc = {}
     reps = 5
     for _ in range(reps):
         rast.flush_l2()
-        frame()
+        frame(c0, c0.scenes[0])
         for k, (us, n) in rast.stage_times_us().items():
             a = stage_acc.setdefault(k, [0.0, 0])
             a[0] += us / reps
             a[1] = n
     rast.enable_stage_timing(False)
     rast.reset_counters()
-    frame()
+    frame(c0, c0.scenes[0])
     counters = rast.counters()
+    draw_stats = rast.draw_stats()
+    exchange = save_exchange
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -246,49 +300,65 @@ def run_ours(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    abytes = algorithmic_bytes(scene, counters)
+    abytes = algorithmic_bytes(scene)
     stages = {}
-    for k in ("mesh", "bin", "raster", "resolve"):
+    for k in ("clear", "mesh", "bin", "raster", "resolve"):
         us = stage_acc.get(k, [0.0, 0])[0]
         if us <= 0:
             continue
+        stages[k] = {"us": round(us, 2)}
         bytes_k = abytes.get(k)
-        stages[k] = {"us": round(us, 2), "launches": stage_acc[k][1]}
         if bytes_k:
             stages[k].update({"algorithmic_bytes": bytes_k, "GBs": round(bytes_k / us / 1e3, 1), "frac": round(bytes_k / us / 1e3 / peak_gbs, 4)})
+    traffic = {}
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     dom = max((k for k in stages if "GBs" in stages[k]), key=lambda k: stages[k]["us"])
     roofline = {"bound": "hbm", "kernel": {"mesh": "k_mesh_setup", "raster": "k_tile_raster" if args.mode == "binned" else "k_raster_direct",
                                             "resolve": "k_resolve"}[dom],
                 "achieved": stages[dom]["GBs"], "peak": peak_gbs, "unit": "GB/s", "frac": stages[dom]["frac"],
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes": stages[dom]["algorithmic_bytes"],
-                "note": "stage time from CUDA events on the launching stream, L2 flushed before each frame"}
+                "avg_launch_us": stages[dom]["us"],
+                "note": "kernel time from CUDA events on the launching stream in latency mode (L2 evicted before each frame); the "
+                        "kernel is instruction-issue bound, not HBM bound (profiles/r01_summary.md)"}
+    roofline["traffic"] = traffic.get(roofline["kernel"])
+    if roofline["traffic"] is not None:
+        roofline["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
 
-    # ---- e2e: the same frame through the C ABI with HOST buffers (rank-local; max over ranks)
-    host_meshlets = rast.alloc_pinned(scene.meshlets.shape, scene.meshlets.dtype)
-    host_meshlets[...] = scene.meshlets
-    host_image = rast.alloc_pinned((scene.height, scene.width), np.uint32)
+    # ---- e2e: the same frames through the C ABI with HOST buffers, F steps in flight
+    for c in ctxs:
+        c.host_meshlets = c.rast.alloc_pinned(scene.meshlets.shape, scene.meshlets.dtype)
+        c.host_meshlets[...] = scene.meshlets
+        c.host_image = c.rast.alloc_pinned((scene.height, scene.width), np.uint32)
 
-    def frame_e2e():
-        gscene.update_meshlets(host_meshlets, 0)          # H2D: 1728 B x meshlets, from pinned memory
-        fb.clear(0xFF000000, 0.0)
-        rast.draw_prebuilt(fb, gscene, batch)
-        rast.resolve(fb, gscene, **uni)
-        fb.get_pixels(0, host_image)                      # D2H: resolved RGBA8 image (synchronises)
+    def frame_e2e(k):
+        c = ctxs[k % F]
+        if c.uses >= 1:
+            c.rast.sync()                                         # this context's previous step (its image is now on the host)
+        c.uses += 1
+        g = c.scenes[0]
+        g.update_meshlets(c.host_meshlets, 0)                     # H2D: 1728 B x meshlets, from pinned memory
+        c.fb.clear(0xFF000000, 0.0)
+        c.rast.draw_prebuilt(c.fb, g, c.batch)
+        c.rast.resolve_prebuilt(c.fb, g, uni_c)
+        c.fb.get_pixels_async(0, c.host_image)                    # D2H: resolved RGBA8 image
 
-    for _ in range(3):
-        frame_e2e()
+    for k in range(3 * F):
+        frame_e2e(k)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        frame_e2e()
+    t0e = time.perf_counter()
+    for k in range(args.steps):
+        frame_e2e(k)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = time.perf_counter() - t0e
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = tris * world * args.steps / e2e_s / 1e6
-    checksum = int(np.bitwise_xor.reduce(host_image.reshape(-1)))
+    checksum = int(np.bitwise_xor.reduce(ctxs[0].host_image.reshape(-1)))
 
     # ---- CPU baseline (rank 0, N=1 only): the reference restatement on the host cores, bounded sample
     cpu = None
@@ -303,24 +373,31 @@ def run_ours(args):
             "config": {"workload": "C2: procedural 999,600-triangle meshlet grid (10,200 meshlets), 1920x1080, "
                                    "clear + vis-buffer (depth + triangle id) + resolve (1 material, 1024^2 2-layer texture, 1 directional light)",
                        "triangles_per_frame": tris, "meshlets": len(scene.meshlets), "mode": args.mode,
-                       "parallelism": f"view-parallel x{world}" + ({"p2p": ", composites stored by each rank's de-tile kernel straight into rank 0's memory over NVLink (peer memory + device-side signals, double-buffered, tail included)", "nccl": ", composites gathered to rank 0 with NCCL on a side stream (double-buffered, tail included)", "none": ""}[gather_kind]),
-                       "l2": "evicted (256 MB write + 256 MB read) before every timed step, outside the step's events",
-                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+                       "frames_in_flight": F,
+                       "parallelism": f"view-parallel x{world}" + {
+                           "p2p": ", composites stored by each rank's de-tile kernel straight into rank 0's memory over NVLink (peer memory + device-side signals, double-buffered, tail included)",
+                           "nccl": ", composites gathered to rank 0 with NCCL on a side stream (double-buffered, tail included)", "none": ""}[gather_kind],
+                       "l2": f"inputs larger than L2: frames rotate over {F * copies} copies of the {scene.meshlets.nbytes / 1e6:.1f} MB meshlet buffer "
+                             f"({F * copies * scene.meshlets.nbytes / 1e6:.0f} MB > 126 MB); latency mode evicts L2 (256 MB write + 256 MB read) before every frame",
+                       "timing": "one CUDA-event pair around the K frames on the launching streams (all contexts joined), max over ranks"},
             "frames_per_s": round(world / (ms_per_step * 1e-3), 1),
-            "step_ms_min_median_max": [round(float(np.min(step_ms)), 5), round(float(np.median(step_ms)), 5), round(float(np.max(step_ms)), 5)],
-            "wall_ms_per_step_incl_flush": round(t_wall / args.steps * 1e3, 4),
+            "latency_ms_per_frame": round(float(np.median(lat_ms)), 5),
+            "latency_ms_min_max": [round(float(np.min(lat_ms)), 5), round(float(np.max(lat_ms)), 5)],
+            "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(scene.meshlets.nbytes + 512),
                     "d2h_bytes_per_step": int(scene.width * scene.height * 4), "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
-                    "note": "meshlets re-uploaded from pinned host memory and the resolved image read back every step; wall clock"},
+                    "note": f"every step: meshlets H2D from pinned host memory, draw + resolve, resolved image D2H to pinned host memory; "
+                            f"{F} steps in flight on separate streams; wall clock"},
             "roofline": roofline, "stages": stages,
             "counters": {k: counters[k] for k in ("TrianglesProcessed", "TrianglesRasterized", "TrianglesClipped", "BinQueueFlushes")},
-            "image_xor": checksum,
+            "draw_stats": draw_stats, "image_xor": checksum,
         }
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    rast.destroy()
+    for c in ctxs:
+        c.rast.destroy()
     if world > 1:
         dist.destroy_process_group()
 
@@ -406,10 +483,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="binned", choices=["binned", "direct"])
+    ap.add_argument("--in-flight", type=int, default=3, help="independent render contexts (frames in flight) per GPU")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -48,6 +48,7 @@ EXPORTS = [
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
     "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
+    "swrb_fb_get_pixels_async",
 ]
 
 
@@ -147,6 +148,10 @@ class Framebuffer:
             out = np.empty((self.height, self.width), dtype=np.uint32)
         _check(self.rast.lib.swrb_fb_get_pixels(self._h, C.c_uint32(layer), _ptr(out), C.c_uint32(out.shape[1])))
         return out
+
+    def get_pixels_async(self, layer: int, out: np.ndarray):
+        """GetPixels without the final synchronisation (`out` should be pinned; valid after Rasterizer.sync())."""
+        _check(self.rast.lib.swrb_fb_get_pixels_async(self._h, C.c_uint32(layer), _ptr(out), C.c_uint32(out.shape[1])))
 
     def get_pixels_device(self, layer: int, device_ptr: int, stride: int | None = None, cuda_stream: int | None = None):
         """GetPixels into device (or NVLink peer) memory; `cuda_stream` launches it on another stream."""
@@ -309,8 +314,9 @@ class Rasterizer:
         _check(self.lib.swrb_draw_meshlets_host(fb._h, _ptr(meshlets), C.c_uint32(len(meshlets)), _ptr(m), _ptr(cb)))
 
     # ShadingContext::Resolve (Shading.cpp:658-689)
-    def resolve(self, fb: Framebuffer, scene: Scene, world_to_clip, object_to_clip, object_to_world3, inv_screen_proj,
-                view_pos, exposure: float = 1.0):
+    @staticmethod
+    def make_uniforms(world_to_clip, object_to_clip, object_to_world3, inv_screen_proj, view_pos, exposure: float = 1.0) -> ShadingUniforms:
+        """The ShadingContext uniform block Resolve reads, as the C struct (build once, reuse per frame)."""
         u = ShadingUniforms()
         u.WorldToClip[:] = _mat(world_to_clip).tolist()
         u.ObjectToClip[:] = _mat(object_to_clip).tolist()
@@ -318,7 +324,15 @@ class Rasterizer:
         u.InvScreenProj[:] = _mat(inv_screen_proj).tolist()
         u.ViewPos[:] = [float(v) for v in view_pos]
         u.Exposure = float(exposure)
+        return u
+
+    def resolve(self, fb: Framebuffer, scene: Scene, world_to_clip, object_to_clip, object_to_world3, inv_screen_proj,
+                view_pos, exposure: float = 1.0):
+        u = self.make_uniforms(world_to_clip, object_to_clip, object_to_world3, inv_screen_proj, view_pos, exposure)
         _check(self.lib.swrb_resolve(fb._h, scene._h, C.byref(u)))
+
+    def resolve_prebuilt(self, fb: Framebuffer, scene: Scene, uniforms: ShadingUniforms):
+        _check(self.lib.swrb_resolve(fb._h, scene._h, C.byref(uniforms)))
 
     def sync(self):
         _check(self.lib.swrb_sync(self._h))

@@ -78,13 +78,26 @@ __global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ src, 
 // x 4 rows = 512 contiguous source bytes.
 __global__ void __launch_bounds__(256)
 k_fb_detile(const uint4* __restrict__ layer, uint32_t* __restrict__ dst, uint32_t width, uint32_t height, uint32_t stride) {
-    uint32_t numVec = width * height / 4;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
-        uint32_t row = i & 3u, tile = i >> 2;
-        uint32_t tilesPerRow = width >> 2;
-        uint32_t tx = tile % tilesPerRow, ty = tile / tilesPerRow;
-        uint4 v = layer[i];
-        *reinterpret_cast<uint4*>(dst + (size_t)(ty * 4 + row) * stride + tx * 4) = v;
+    const uint32_t numVec = width * height / 4, tilesPerRow = width >> 2;
+    const uint32_t step = gridDim.x * blockDim.x;
+    // four independent loads in flight per thread: with a small grid (the peer-memory gather runs beside the
+    // render kernels and must not take their SMs) the copy still keeps enough bytes in flight for NVLink
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < numVec; i0 += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t i = i0 + k * step;
+            if (i < numVec) v[k] = layer[i];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t i = i0 + k * step;
+            if (i < numVec) {
+                uint32_t row = i & 3u, tile = i >> 2;
+                uint32_t tx = tile % tilesPerRow, ty = tile / tilesPerRow;
+                *reinterpret_cast<uint4*>(dst + (size_t)(ty * 4 + row) * stride + tx * 4) = v[k];
+            }
+        }
     }
 }
 

@@ -78,7 +78,7 @@ __device__ __forceinline__ void raster_inline(const TriRecord& t, const BBox& r,
 }
 
 template <bool kBinned>
-__global__ void __launch_bounds__(kMeshWarps * 32, 3)
+__global__ void __launch_bounds__(kMeshWarps * 32, 4)      // 64 registers: 4 blocks = 32 warps per SM
 k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
              const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
              unsigned long long* __restrict__ keys,

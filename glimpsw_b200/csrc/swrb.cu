@@ -501,7 +501,11 @@ static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, u
     int rc = fb_materialize_for_read(fb, layer);
     if (rc) return rc;
     uint32_t numVec = fb->width * fb->height / 4;
-    k_fb_detile<<<grid_for(d, numVec, 256, 8), 256, 0, stream>>>(
+    // On the device's own stream the copy is on the critical path: fill the machine. On a caller's side
+    // stream it runs beside the render kernels (typically storing to a peer GPU over NVLink): one block per
+    // SM, four loads in flight per thread.
+    const uint32_t grid = stream == d->stream ? grid_for(d, numVec, 256, 8) : std::max(1u, (uint32_t)d->numSMs);
+    k_fb_detile<<<grid, 256, 0, stream>>>(
         reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride);
     d->launches++;
     CU(cudaGetLastError());
@@ -518,7 +522,7 @@ int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_d
     return get_pixels_device_on(fb, layer, dst_device, stride, (cudaStream_t)cuda_stream);
 }
 
-int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {
+int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {
     if (!fb || !dst_host) return fail(SWRB_E_INVALID, "null argument");
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
@@ -532,8 +536,14 @@ int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t
     int rc = swrb_fb_get_pixels_device(fb, layer, d->detileScratch, fb->width);
     if (rc) return rc;
     CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch, (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->stream));
-    CU(cudaStreamSynchronize(d->stream));
-    return check_overflow(d);
+    return SWRB_OK;
+}
+
+int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {
+    int rc = swrb_fb_get_pixels_async(fb, layer, dst_host, stride);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(fb->dev->stream));
+    return check_overflow(fb->dev);
 }
 
 // ---- culling -----------------------------------------------------------------------------------
