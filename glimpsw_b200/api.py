@@ -48,7 +48,8 @@ EXPORTS = [
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
     "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
-    "swrb_fb_get_pixels_async",
+    "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
+    "swrb_hiz_download", "swrb_cull_meshlets_hiz",
 ]
 
 
@@ -93,7 +94,8 @@ def load_library() -> C.CDLL:
         lib.swrb_device_destroy.restype = None
         lib.swrb_scene_destroy.restype = None
         lib.swrb_fb_destroy.restype = None
-        for name in ("swrb_device_destroy", "swrb_scene_destroy", "swrb_fb_destroy"):
+        lib.swrb_hiz_destroy.restype = None
+        for name in ("swrb_device_destroy", "swrb_scene_destroy", "swrb_fb_destroy", "swrb_hiz_destroy"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.swrb_device_reserve.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         _lib = lib
@@ -220,6 +222,41 @@ class Scene:
             pass
 
 
+class DepthPyramid:
+    """The half-resolution R32f min pyramid of the previous frame's depth (Main.cpp:54-56, ImageHelpers.cpp:150-247)."""
+
+    def __init__(self, rast: "Rasterizer", fb_width: int, fb_height: int):
+        self.rast = rast
+        self._h = C.c_void_p()
+        _check(rast.lib.swrb_hiz_create(rast._h, C.c_uint32(fb_width), C.c_uint32(fb_height), C.byref(self._h)))
+        d = TextureDesc()
+        _check(rast.lib.swrb_hiz_info(self._h, C.byref(d)))
+        self.width, self.height, self.mip_levels, self.row_shift = d.Width, d.Height, d.MipLevels, d.RowShift
+        self.layer_stride = d.LayerStride
+        self.mip_offsets = np.array(list(d.MipOffsets), dtype=np.uint32)
+        rast._children.add(self)
+
+    def build(self, fb: Framebuffer):
+        """texutil::DownsampleDepth(fb, self)."""
+        _check(self.rast.lib.swrb_hiz_build(self._h, fb._h))
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.layer_stride, dtype=np.float32)
+        _check(self.rast.lib.swrb_hiz_download(self._h, _ptr(out)))
+        return out
+
+    def destroy(self):
+        if self._h:
+            self.rast.lib.swrb_hiz_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class Rasterizer:
     """swr::Rasterizer (Rasterizer.h:202-340) bound to one CUDA device."""
 
@@ -257,6 +294,19 @@ class Rasterizer:
         _check(self.lib.swrb_cull_meshlets(scene._h, C.c_uint32(offset), C.c_uint32(count), _ptr(_mat(proj)),
                                            _ptr(_mat(view)), _ptr(_mat(model)), _ptr(bitmap),
                                            C.byref(vis) if download else None))
+        return bitmap, vis.value
+
+    # HiZ occlusion culling: texutil::DownsampleDepth + the HiZ half of ShadingContext::CullMeshlets
+    def create_hiz(self, fb_width: int, fb_height: int) -> "DepthPyramid":
+        return DepthPyramid(self, fb_width, fb_height)
+
+    def cull_meshlets_hiz(self, scene: Scene, offset: int, count: int, proj, view, model, prev_view, frame_w: int, frame_h: int,
+                          hiz: "DepthPyramid | None" = None, download: bool = True):
+        bitmap = np.zeros((count + 15) // 16, dtype=np.uint16) if download else None
+        vis = C.c_uint32(0)
+        _check(self.lib.swrb_cull_meshlets_hiz(scene._h, C.c_uint32(offset), C.c_uint32(count), _ptr(_mat(proj)), _ptr(_mat(view)),
+                                               _ptr(_mat(model)), _ptr(_mat(prev_view)), C.c_float(frame_w), C.c_float(frame_h),
+                                               hiz._h if hiz is not None else None, _ptr(bitmap), C.byref(vis) if download else None))
         return bitmap, vis.value
 
     def frustum_planes(self, proj, view, model) -> np.ndarray:

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "cull.cuh"
+#include "hiz.cuh"
 #include "bin.cuh"
 #include "mesh.cuh"
 #include "tile.cuh"
@@ -608,6 +609,131 @@ int swrb_cull_meshlets(swrb_scene* s, uint32_t meshlet_offset, uint32_t count, c
             // the kernel writes whole u32 words; copy only the u16 words the caller's array has
             CU(cudaMemcpyAsync(bitmap_out_host, d->cullBitmapDev, (size_t)((count + 15) / 16) * 2, cudaMemcpyDeviceToHost, d->stream));
         }
+        uint32_t vis = 0;
+        CU(cudaMemcpyAsync(&vis, d->visibleDev, 4, cudaMemcpyDeviceToHost, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+        if (visible_out) *visible_out = vis;
+    }
+    return SWRB_OK;
+}
+
+// ---- HiZ occlusion culling ---------------------------------------------------------
+struct swrb_hiz {
+    swrb_device* dev;
+    HizDesc desc;
+    uint32_t layerStride;     // texels
+};
+
+int swrb_hiz_create(swrb_device* d, uint32_t fb_width, uint32_t fb_height, swrb_hiz** out) {
+    if (!d || !out || fb_width < 16 || fb_height < 16) return fail(SWRB_E_INVALID, "bad argument");
+    CU(cudaSetDevice(d->cudaDevice));
+    auto bit_length = [](uint32_t v) { uint32_t n = 0; while (v) { n++; v >>= 1; } return n; };
+    // Main.cpp:54-56: halfW = 1 << (32 - lzcnt((width - 1) / 2)); CreateTexture2D<R32f>(halfW, halfH, 16)
+    uint32_t w = 1u << bit_length((fb_width - 1) / 2), h = 1u << bit_length((fb_height - 1) / 2);
+    swrb_hiz* z = new swrb_hiz();
+    z->dev = d;
+    z->desc.width = w; z->desc.height = h;
+    z->desc.rowShift = 0;
+    while ((1u << z->desc.rowShift) < std::max(w, 8u)) z->desc.rowShift++;                 // Texture.h:602
+    uint32_t stride = 0, mip = 0;
+    for (; mip < 16; mip++) {                                                             // Texture.h:607-612
+        if ((w >> mip) < 4 || (h >> mip) < 4) break;
+        z->desc.mipOffsets[mip] = stride;
+        stride += ((w >> mip) * (h >> mip) + 63u) & ~63u;
+    }
+    for (uint32_t k = mip; k < 16; k++) z->desc.mipOffsets[k] = 0;
+    z->desc.mipLevels = mip;
+    z->layerStride = stride;
+    CU(cudaMalloc(&z->desc.data, (size_t)stride * 4 + 256));
+    CU(cudaMemsetAsync(z->desc.data, 0, (size_t)stride * 4, d->stream));
+    *out = z;
+    return SWRB_OK;
+}
+
+void swrb_hiz_destroy(swrb_hiz* z) {
+    if (!z) return;
+    cudaSetDevice(z->dev->cudaDevice);
+    cudaStreamSynchronize(z->dev->stream);
+    cudaFree(z->desc.data);
+    delete z;
+}
+
+int swrb_hiz_info(const swrb_hiz* z, swr_texture_desc* out) {
+    if (!z || !out) return fail(SWRB_E_INVALID, "null argument");
+    out->Width = z->desc.width; out->Height = z->desc.height; out->MipLevels = z->desc.mipLevels; out->NumLayers = 1;
+    out->RowShift = z->desc.rowShift; out->LayerStride = z->layerStride; out->Data = nullptr;
+    for (int k = 0; k < 16; k++) out->MipOffsets[k] = z->desc.mipOffsets[k];
+    return SWRB_OK;
+}
+
+// texutil::DownsampleDepth(fb, depthMap) (ImageHelpers.cpp:243-247)
+int swrb_hiz_build(swrb_hiz* z, swrb_fb* fb) {
+    if (!z || !fb) return fail(SWRB_E_INVALID, "null argument");
+    if (z->dev != fb->dev) return fail(SWRB_E_INVALID, "pyramid and framebuffer belong to different devices");
+    swrb_device* d = z->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    int rc = fb_materialize_for_read(fb, 1);
+    if (rc) return rc;
+    uint32_t maxDim = std::max(fb->width, fb->height), rootLevel = 0;
+    while ((1u << rootLevel) <= maxDim) rootLevel++;                                      // 32 - lzcnt(max(W,H))
+    StageScope ss(d, SWRB_STAGE_CULL);
+    for (uint32_t m = 0; m + 3 <= rootLevel && m < z->desc.mipLevels; m++) {
+        const bool top = (m + 3 == rootLevel);
+        const uint32_t texel = 1u << (m + 1), blockPx = (top ? 4u : 8u) * texel;
+        uint32_t tx = top ? 4u : ((fb->width + blockPx - 1) / blockPx) * 8u, ty = top ? 4u : ((fb->height + blockPx - 1) / blockPx) * 8u;
+        dim3 grid((tx + 31) / 32, (ty + 7) / 8);
+        k_hiz_level<<<grid, 256, 0, d->stream>>>(reinterpret_cast<const float*>(fb->data + fb->layerStride), z->desc, m, fb->width, fb->height, tx, ty);
+        d->launches++;
+    }
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+int swrb_hiz_download(swrb_hiz* z, float* dst_host) {
+    if (!z || !dst_host) return fail(SWRB_E_INVALID, "null argument");
+    CU(cudaSetDevice(z->dev->cudaDevice));
+    CU(cudaMemcpyAsync(dst_host, z->desc.data, (size_t)z->layerStride * 4, cudaMemcpyDeviceToHost, z->dev->stream));
+    CU(cudaStreamSynchronize(z->dev->stream));
+    return SWRB_OK;
+}
+
+// ShadingContext::CullMeshlets(bitmap, meshlets, count, P, V, M, prevV, frameSize, depthMap) — Shading.cpp:775-869
+int swrb_cull_meshlets_hiz(swrb_scene* s, uint32_t meshlet_offset, uint32_t count, const float proj[16], const float view[16],
+                           const float model[16], const float prev_view[16], float frame_w, float frame_h, swrb_hiz* hiz,
+                           uint16_t* bitmap_out_host, uint32_t* visible_out) {
+    if (!s || !proj || !view || !model) return fail(SWRB_E_INVALID, "null argument");
+    if ((uint64_t)meshlet_offset + count > s->numMeshlets) return fail(SWRB_E_INVALID, "meshlet range out of bounds");
+    if (hiz && (!prev_view || hiz->dev != s->dev)) return fail(SWRB_E_INVALID, "HiZ culling needs prev_view and a pyramid of the same device");
+    swrb_device* d = s->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    CullHizParams cp;
+    int rc = swrb_frustum_planes(proj, view, model, cp.planes);
+    if (rc) return rc;
+    HizDesc hz{};
+    cp.useHiz = hiz ? 1 : 0;
+    cp.frameW = frame_w; cp.frameH = frame_h;
+    cp.scale = sqrtf((model[0] * model[0] + model[1] * model[1]) + model[2] * model[2]);   // glm::length(vec3(modelMat[0]))
+    cp.znear = proj[3 * 4 + 2]; cp.p00 = proj[0]; cp.p11 = proj[1 * 4 + 1];
+    if (hiz) { mat4_mul(prev_view, model, cp.objectToPrevView); hz = hiz->desc; }
+    else memset(cp.objectToPrevView, 0, sizeof(cp.objectToPrevView));
+    uint32_t words32 = (count + 31) / 32;
+    if (d->cullBitmapCap < words32 * 32 || !d->cullBitmapDev) {
+        if (d->cullBitmapDev) CU(cudaFree(d->cullBitmapDev));
+        d->cullBitmapDev = nullptr;
+        CU(cudaMalloc(&d->cullBitmapDev, (size_t)std::max(words32, 1u) * 4));
+        d->cullBitmapCap = words32 * 32;
+    }
+    CU(cudaMemsetAsync(d->visibleDev, 0, 4, d->stream));
+    if (count) {
+        StageScope ss(d, SWRB_STAGE_CULL);
+        k_cull_meshlets_hiz<<<(count + 255) / 256, 256, 0, d->stream>>>(s->meshlets + meshlet_offset, count, cp, hz,
+                                                                        reinterpret_cast<uint32_t*>(d->cullBitmapDev), d->visibleDev);
+        d->launches++;
+        CU(cudaGetLastError());
+    }
+    if (bitmap_out_host || visible_out) {
+        if (bitmap_out_host && count)
+            CU(cudaMemcpyAsync(bitmap_out_host, d->cullBitmapDev, (size_t)((count + 15) / 16) * 2, cudaMemcpyDeviceToHost, d->stream));
         uint32_t vis = 0;
         CU(cudaMemcpyAsync(&vis, d->visibleDev, 4, cudaMemcpyDeviceToHost, d->stream));
         CU(cudaStreamSynchronize(d->stream));

@@ -122,6 +122,22 @@ SWRB_API int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, vo
 SWRB_API int swrb_cull_meshlets(swrb_scene* scene, uint32_t meshlet_offset, uint32_t count,
                                 const float proj[16], const float view[16], const float model[16],
                                 uint16_t* bitmap_out_host, uint32_t* visible_out);
+/* HiZ occlusion culling (the reference's second half of CullMeshlets):
+ *   swrb_hiz_create   the R32f TiledY8 depth pyramid the Playground allocates, CreateTexture2D<R32f>(halfW, halfH, 16)
+ *                     with halfW/halfH from Main.cpp:54-56
+ *   swrb_hiz_build    texutil::DownsampleDepth(fb, depthMap)  (ImageHelpers.cpp:150-247)
+ *   swrb_cull_meshlets_hiz   ShadingContext::CullMeshlets(bitmap, meshlets, count, P, V, M, prevV, frameSize, depthMap)
+ *                     (Shading.cpp:775-869) — hiz == NULL gives the frustum-only result of swrb_cull_meshlets. */
+typedef struct swrb_hiz swrb_hiz;
+SWRB_API int swrb_hiz_create(swrb_device* dev, uint32_t fb_width, uint32_t fb_height, swrb_hiz** out);
+SWRB_API void swrb_hiz_destroy(swrb_hiz* hiz);
+SWRB_API int swrb_hiz_info(const swrb_hiz* hiz, swr_texture_desc* out);    /* layout (Data = NULL) */
+SWRB_API int swrb_hiz_build(swrb_hiz* hiz, swrb_fb* fb);
+SWRB_API int swrb_hiz_download(swrb_hiz* hiz, float* dst_host);            /* LayerStride floats, raw TiledY8 */
+SWRB_API int swrb_cull_meshlets_hiz(swrb_scene* scene, uint32_t meshlet_offset, uint32_t count,
+                                    const float proj[16], const float view[16], const float model[16], const float prev_view[16],
+                                    float frame_w, float frame_h, swrb_hiz* hiz,
+                                    uint16_t* bitmap_out_host, uint32_t* visible_out);
 /* The five normalised Gribb-Hartmann planes CullMeshlets tests (Shading.cpp:783-791, :806). */
 SWRB_API int swrb_frustum_planes(const float proj[16], const float view[16], const float model[16], float planes_out[5][4]);
 

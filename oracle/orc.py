@@ -169,6 +169,34 @@ class Baseline:
             pass
 
 
+def hiz_dims(width: int, height: int):
+    """Size of the R32f depth pyramid the Playground allocates (Main.cpp:54-56)."""
+    half_w = 1 << int((width - 1) // 2).bit_length()
+    half_h = 1 << int((height - 1) // 2).bit_length()
+    return half_w, half_h
+
+
+def downsample_depth(fb: Framebuffer, pyramid) -> None:
+    """texutil::DownsampleDepth on the CPU: fb layer 1 -> `pyramid` (glimpsw_b200.textures.TextureData, R32f bits)."""
+    descs, keep = _texture_descs([pyramid])
+    data = keep[0]
+    lib().orc_downsample_depth(_p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), descs, _p(data))
+    pyramid.data = data
+
+
+def cull_meshlets_hiz(meshlets: np.ndarray, proj, view, model, prev_view, frame_w: int, frame_h: int, pyramid=None):
+    """ShadingContext::CullMeshlets incl. the HiZ test (pyramid=None: frustum part only). Returns (bitmap, visible)."""
+    bitmap = np.zeros((len(meshlets) + 15) // 16, dtype=np.uint16)
+    descs, data = None, None
+    if pyramid is not None:
+        descs, keep = _texture_descs([pyramid])
+        data = _p(keep[0])
+    lib().orc_cull_meshlets_hiz.restype = C.c_uint32
+    n = lib().orc_cull_meshlets_hiz(_p(bitmap), _p(meshlets), C.c_uint32(len(meshlets)), _p(_mat(proj)), _p(_mat(view)),
+                                    _p(_mat(model)), _p(_mat(prev_view)), C.c_float(frame_w), C.c_float(frame_h), descs, data)
+    return bitmap, int(n)
+
+
 def frustum_planes(proj, view, model) -> np.ndarray:
     out = np.zeros((6, 4), dtype=np.float32)
     lib().orc_frustum_planes(_p(_mat(proj)), _p(_mat(view)), _p(_mat(model)), _p(out))
