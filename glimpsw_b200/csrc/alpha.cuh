@@ -22,7 +22,8 @@ namespace swrb {
 __global__ void __launch_bounds__(256)
 k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict__ trisW, FrameParams fp,
                const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
-               const ResolveTexture* __restrict__ textures, unsigned long long* __restrict__ keys, DevCtl* __restrict__ ctl) {
+               const ResolveTexture* __restrict__ textures, const float4* __restrict__ clipRemap,
+               unsigned long long* __restrict__ keys, DevCtl* __restrict__ ctl) {
     const uint32_t n = ctl->overflow ? 0u : ctl->alphaCount;
     const uint32_t lane = lane_id(), i = lane & 15u, half = 0xFFFFu << (lane & 16u);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
@@ -33,6 +34,9 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
         t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
         t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(trisW + it));
+        const bool clipped = t.aux == 2u;                                             // a piece from k_clip_triangles: DrawTriangle<FS, true>
+        float4 ruv0 = make_float4(0.0f, 1.0f, 0.0f, 0.0f), ruv1 = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
+        if (clipped) { ruv0 = __ldg(clipRemap + 2 * it); ruv1 = __ldg(clipRemap + 2 * it + 1); }
 
         const swr_meshlet* mesh = meshlets + (t.id / SWR_MAX_PRIMS);
         const uint32_t prim = t.id % SWR_MAX_PRIMS;
@@ -78,6 +82,11 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
             rcpW = __fmul_rn(rcpW, __fmaf_rn(-w, rcpW, 2.0f));
             u = __fmul_rn(u, __fmul_rn(W1S, rcpW));
             v = __fmul_rn(v, __fmul_rn(W2S, rcpW));
+            if (clipped) {                                                            // ClippedU / ClippedV remap (Rasterizer.h:312-318)
+                const float cu = __fmaf_rn(u, ruv0.y, __fmaf_rn(v, ruv0.z, ruv0.x));
+                const float cv = __fmaf_rn(u, ruv1.x, __fmaf_rn(v, ruv1.y, ruv0.w));
+                u = cu; v = cv;
+            }
             const float b0 = __fsub_rn(__fsub_rn(1.0f, u), v);
             const float tu = __fmaf_rn(uv[0][0], b0, __fmaf_rn(uv[1][0], u, __fmul_rn(uv[2][0], v)));   // BaryLerp, Rasterizer.h:101-104
             const float tv = __fmaf_rn(uv[0][1], b0, __fmaf_rn(uv[1][1], u, __fmul_rn(uv[2][1], v)));

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256)
 k_frame_begin(const uint4* __restrict__ depthLayer, uint32_t clearDepthBits, ulonglong2* __restrict__ keys, uint32_t numVec,
               uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileCursor, uint32_t numTiles, DevCtl* __restrict__ ctl) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; }
+    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0; }
     for (uint32_t i = gid; i < numTiles; i += stride) { tileCount[i] = 0; tileCursor[i] = 0; }
     for (uint32_t i = gid; i < numVec; i += stride) {
         uint4 d = make_uint4(clearDepthBits, clearDepthBits, clearDepthBits, clearDepthBits);

@@ -7,7 +7,7 @@
 //   GatherPos / index widen      Rasterizer.cpp:143-151, :553-558
 //   Clipper::ComputeClipCodes    Rasterizer.cpp:353-397
 //   TrianglePacket::Setup + bbox Rasterizer.cpp:257-289, :331-351
-// and, for small and medium triangles, also
+// and, for triangles whose pixel region is <= kInlineMaxArea, also
 //   TriangleEdgeVars::Setup      Rasterizer.cpp:296-329
 //   DrawTriangle<> + FS_EncodeSurfaceId<false>   Rasterizer.h:250-328, Shading.cpp:309-331
 //
@@ -83,7 +83,8 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
              const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
              unsigned long long* __restrict__ keys,
              TriRecord* __restrict__ tris, TriRecord* __restrict__ alphaTris, TriRecordW* __restrict__ alphaW, uint32_t triCapacity,
-             uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, DevCtl* __restrict__ ctl) {
+             uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint2* __restrict__ clipList,
+             DevCtl* __restrict__ ctl) {
     __shared__ MeshWarpSmem smem[kMeshWarps];
     MeshWarpSmem& s = smem[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -223,7 +224,19 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             const uint32_t lt = (1u << lane) - 1u;
             if (big) s.big[numBig + __popc(bigMask & lt)] = (uint8_t)prim;
             numBig += __popc(bigMask);
-            if (lane == 0) { nRasterized += __popc(keepMask); nClipped += __popc(clipMask); }   // :579, :568
+            if (lane == 0) { nRasterized += __popc(keepMask); nClipped += fp.clipMode != 1u ? __popc(clipMask) : 0; }   // :579, :568 / :210
+            if (!kBinned && fp.clipMode == 2u && clipMask) {
+                // EnableClipping on the unbinned path (Rasterizer.cpp:209-249): name the triangle in the clip list;
+                // k_clip_triangles re-derives its clip-space vertices, clips and appends the pieces as records
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&ctl->clipCount, (uint32_t)__popc(clipMask));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (nonTrivial) {
+                    const uint32_t slot = base + __popc(clipMask & lt);
+                    if (slot < triCapacity) clipList[slot] = make_uint2((uint32_t)(&d - draws), (meshIdx << 7) | prim);
+                    else atomicExch(&ctl->overflow, 1u);
+                }
+            }
         }
         if (numBig) __syncwarp();
 

@@ -26,6 +26,7 @@
 #include "fbops.cuh"
 #include "resolve.cuh"
 #include "alpha.cuh"
+#include "clip.cuh"
 
 using namespace swrb;
 
@@ -67,6 +68,7 @@ struct swrb_device {
     TriRecord* tris = nullptr;
     TriRecord* alphaTris = nullptr;   // alpha-tested triangles (only allocated for scenes with AlphaCutoff < 255 materials)
     TriRecordW* trisW = nullptr;      // their 1/w
+    float4* clipRemap = nullptr;      // ClippedU/ClippedV of clipped alpha-tested pieces (2 float4 per alpha record)
     uint32_t* bigList = nullptr;      // binned: big triangle indices (capacity triCap)
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
@@ -239,7 +241,7 @@ void swrb_device_destroy(swrb_device* d) {
     if (!d) return;
     cudaSetDevice(d->cudaDevice);
     cudaStreamSynchronize(d->stream);
-    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->alphaTris); cudaFree(d->bigList);
+    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->clipRemap); cudaFree(d->alphaTris); cudaFree(d->bigList);
     cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
@@ -753,6 +755,7 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
         if (d->bigList) { CU(cudaFree(d->bigList)); d->bigList = nullptr; }
         CU(cudaMalloc(&d->bigList, needTris * 4));
         if (d->trisW) { CU(cudaFree(d->trisW)); d->trisW = nullptr; }
+        if (d->clipRemap) { CU(cudaFree(d->clipRemap)); d->clipRemap = nullptr; }
         if (d->alphaTris) { CU(cudaFree(d->alphaTris)); d->alphaTris = nullptr; }
         d->triCap = needTris;
     }
@@ -760,6 +763,8 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
         CU(cudaMalloc(&d->trisW, d->triCap * sizeof(TriRecordW)));
         CU(cudaMalloc(&d->alphaTris, d->triCap * sizeof(TriRecord)));
     }
+    const bool clipping = !(d->flags & SWRB_FLAG_BINNING) && (d->flags & SWRB_FLAG_CLIPPING);
+    if (alphaTest && clipping && !d->clipRemap) CU(cudaMalloc(&d->clipRemap, d->triCap * 2 * sizeof(float4)));
     uint64_t needBins = std::max<uint64_t>(d->reserveBins, 2 * d->triCap + (1u << 20));
     if (needBins > d->binCap) {
         int rc = ensure_buffer((void**)&d->binEntries, &d->binCap, needBins, 4);
@@ -795,6 +800,7 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
     fp.tilesX = (fb->width + kTileSize - 1) >> kTileShift;
     fp.tilesY = (fb->height + kTileSize - 1) >> kTileShift;
     fp.layerStride = fb->layerStride;
+    fp.clipMode = binned ? 0u : ((d->flags & SWRB_FLAG_CLIPPING) ? 2u : 1u);          // :567-569 vs :209
     return fp;
 }
 
@@ -897,7 +903,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, d->ctl);
+                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, nullptr, d->ctl);
             d->launches++;
         }
         {
@@ -917,8 +923,14 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                            d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr, d->ctl);
+                                                                            d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr,
+                                                                            reinterpret_cast<uint2*>(d->binEntries), d->ctl);   // (the bin-entry buffer is idle on this path)
             d->launches++;
+            if (fp.clipMode == 2u) {       // Clipper::ClipTriangles: pieces join the record / alpha lists before they are consumed
+                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, d->drawItems, fp,
+                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, (uint32_t)d->triCap, d->ctl);
+                d->launches++;
+            }
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
@@ -929,7 +941,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     }
     if (alphaTest && texturesDev != nullptr) {     // FS_EncodeSurfaceId<true> for the alpha list (both raster modes)
         StageScope ss(d, SWRB_STAGE_RASTER);
-        k_raster_alpha<<<d->numSMs * 4, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, fb->keys, d->ctl);
+        k_raster_alpha<<<d->numSMs * 4, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, fb->keys, d->ctl);
         d->launches++;
     }
     // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the

@@ -441,6 +441,17 @@ def room_scene(width: int = 1920, height: int = 1080, subdiv: int = 5, size: flo
     return SceneData(f"room{subdiv}", meshlets, [DrawNode(0, len(meshlets), cam.identity())], camera, width, height)
 
 
+def closeup_alpha_scene(width: int = 960, height: int = 540, nu: int = 40, nv: int = 10, tex_size: int = 128) -> SceneData:
+    """Clipper stress: a coarse torus knot (big triangles) with an alpha-tested, double-sided second material,
+    seen from a camera that sits just above the tube surface — dozens of triangles of both materials cross the
+    camera plane (w < near) or leave the guard band, so the unbinned path has to clip them and, for the
+    alpha-tested ones, remap the barycentrics of every piece (Rasterizer.h:312-318)."""
+    scene = torus_knot_scene(nu, nv, width, height, tex_size=tex_size, alpha_material=True)
+    scene.name = f"closeup_alpha{nu}x{nv}"
+    scene.camera = cam.Camera(position=(1.07735, 0.19206, -0.15236), euler=(4.71, 0.0), fov_deg=100.0, aspect=width / height, near_z=0.05)
+    return scene
+
+
 def resolve_uniforms(scene: SceneData, node: DrawNode, exposure: float = 1.0) -> dict:
     """The ShadingContext fields Resolve reads (Shading.h:21-33, Shading.cpp:659)."""
     proj, view = scene.view_proj()

@@ -176,6 +176,58 @@ inline int clip_codes(const Vec4 v[3], float bx, float by, uint8_t* outcodes) {
     return (visible && trivial ? 1 : 0) | (visible && !trivial ? 2 : 0);
 }
 
+// Clipper::ClipTriangles for one lane — Rasterizer.cpp:398-478 (Sutherland-Hodgman against the planes named
+// by the triangle's partial outcodes, ascending plane id; x/y planes sit on the guard band, z planes on the
+// frustum; the result polygon is fan-triangulated). attr[4]/attr[5] carry the barycentric weights of v1/v2.
+// Returns the number of output triangles (<= 7); tris[n][3] in clip space, remapU/V[n] = ClippedU/ClippedV.
+struct ClipVert { float a[6]; };
+inline float clip_dist(const ClipVert& v, uint32_t planeId, float scale) {   // GetIntersectDist, :76-81
+    float a = v.a[planeId / 2];
+    if (planeId % 2) a = -a;
+    return a + v.a[3] * scale;
+}
+inline int clip_triangle(const Vec4 v[3], uint8_t outcodes, float bx, float by,
+                         Vec4 tris[7][3], float remapU[7][3], float remapV[7][3]) {
+    ClipVert verts[64];
+    uint8_t indices[32];
+    for (int i = 0; i < 3; i++) {
+        verts[i] = { { v[i].x, v[i].y, v[i].z, v[i].w, i == 1 ? 1.0f : 0.0f, i == 2 ? 1.0f : 0.0f } };
+        indices[i] = (uint8_t)i;
+    }
+    uint32_t vertCount = 3, nextIdx = 3;
+    for (uint32_t planeId = 0; planeId < 6; planeId++) {                     // BitIter(OutCodes) — ascending bits
+        if (!((outcodes >> planeId) & 1)) continue;
+        uint8_t outIndices[32];
+        uint32_t outCount = 0;
+        float planeScale = planeId < 4 ? (planeId / 2 == 0 ? bx : by) : 1.0f;      // :422
+        for (uint32_t vi = 0; vi < vertCount; vi++) {
+            uint8_t ia = indices[vi], ib = indices[(vi + 1) % vertCount];
+            float da = clip_dist(verts[ia], planeId, planeScale);
+            float db = clip_dist(verts[ib], planeId, planeScale);
+            if (da >= 0) outIndices[outCount++] = ia;
+            if ((da >= 0) != (db >= 0)) {                                    // :432-439
+                float t = da / (da - db);
+                for (int k = 0; k < 6; k++) verts[nextIdx].a[k] = std::fmaf(verts[ib].a[k], t, std::fmaf(-t, verts[ia].a[k], verts[ia].a[k]));
+                outIndices[outCount++] = (uint8_t)nextIdx++;
+            }
+        }
+        if (vertCount < 3) break;                                            // :443 (tests the count before this plane)
+        vertCount = outCount;
+        memcpy(indices, outIndices, sizeof(indices));
+    }
+    if (vertCount < 3) return 0;                                             // :448 + the empty fan loop for 2 vertices
+    int n = 0;
+    for (uint32_t vi = 0; vi < vertCount - 2; vi++, n++) {                   // :451-466
+        const ClipVert &p0 = verts[indices[0]], &p1 = verts[indices[vi + 1]], &p2 = verts[indices[vi + 2]];
+        tris[n][0] = { p0.a[0], p0.a[1], p0.a[2], p0.a[3] };
+        tris[n][1] = { p1.a[0], p1.a[1], p1.a[2], p1.a[3] };
+        tris[n][2] = { p2.a[0], p2.a[1], p2.a[2], p2.a[3] };
+        remapU[n][0] = p0.a[4]; remapU[n][1] = p1.a[4] - p0.a[4]; remapU[n][2] = p2.a[4] - p0.a[4];
+        remapV[n][0] = p0.a[5]; remapV[n][1] = p1.a[5] - p0.a[5]; remapV[n][2] = p2.a[5] - p0.a[5];
+    }
+    return n;
+}
+
 inline uint32_t fb_pixel_offset(uint32_t x, uint32_t y, uint32_t width) {   // Rasterizer.h:50-56
     return ((x & ~3u) << 2) + (y & ~3u) * width + (x & 3) + (y & 3) * 4;
 }
@@ -225,7 +277,8 @@ inline float half_to_float(uint16_t h) {   // _mm_cvtph_ps (exact)
 // Canonical arithmetic for the perspective correction: approx_rcp -> 1/w, then the source's Newton step.
 inline void draw_triangle_alpha(uint32_t* color, float* depth, uint32_t width, const TriEdges& e,
                                 uint32_t bbMin, uint32_t bbMax, uint32_t surfaceId, const uint32_t packedTC[3],
-                                const swr_texture_desc* tex, uint32_t alphaCutoff) {
+                                const swr_texture_desc* tex, uint32_t alphaCutoff,
+                                const float* clipU = nullptr, const float* clipV = nullptr) {
     uint32_t minX = bbMin & 0xFFFF, minY = bbMin >> 16, maxX = bbMax & 0xFFFF, maxY = bbMax >> 16;
     float uv[3][2];
     for (int k = 0; k < 3; k++) {                                                     // UnpackHalf2x16 (Shading.cpp:227-230)
@@ -253,6 +306,11 @@ inline void draw_triangle_alpha(uint32_t* color, float* depth, uint32_t width, c
                 rcpW *= std::fmaf(-w, rcpW, 2.0f);
                 u *= e.W1S * rcpW;
                 v *= e.W2S * rcpW;
+                if (clipU != nullptr) {                                                // IsClipped, Rasterizer.h:312-318
+                    float cu = std::fmaf(u, clipU[1], std::fmaf(v, clipU[2], clipU[0]));
+                    float cv = std::fmaf(u, clipV[1], std::fmaf(v, clipV[2], clipV[0]));
+                    u = cu, v = cv;
+                }
                 float b0 = 1 - u - v;
                 // vars.Interpolate = BaryLerp (Rasterizer.h:101-104), v0,v1,v2 = VertexId[0..2]
                 tu[i] = std::fmaf(uv[0][0], b0, std::fmaf(uv[1][0], u, uv[2][0] * v));
@@ -340,6 +398,10 @@ int orc_probe_triangle(const float* v, uint32_t width, uint32_t height, int cull
 //   color/depth : layer 0 / layer 1 of a 4x4-tiled framebuffer (Rasterizer.h:10-63)
 //   meshlets    : scene base pointer; the draw covers [meshletOffset, meshletOffset+count)
 //   flags bit0  : guard band enabled (the binned path always enables it, Rasterizer.cpp:509)
+//   flags bit1  : EnableClipping on the unbinned path (DrawMeshletsST, Rasterizer.cpp:209-249): non-trivial
+//                 triangles go through Clipper::ClipTriangles and DrawTriangle<FS, true>
+//   flags bit2  : unbinned path with clipping off — non-trivial triangles are dropped WITHOUT being counted
+//                 (the TrianglesClipped increment sits inside the EnableClipping branch, :209-210)
 //   counters[4] : TrianglesProcessed, TrianglesRasterized, TrianglesClipped, (unused) — accumulated
 // `textures` == NULL: alpha-tested materials (FragmentShaderId 1) are drawn with the opaque program.
 // Otherwise they run FS_EncodeSurfaceId<true> (draw_triangle_alpha above); the sampler itself lives in
@@ -367,37 +429,63 @@ void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_
     float bx = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)width : 1.0f;             // :509
     float by = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)height : 1.0f;
     static swr_shaded_meshlet mesh;   // (single-threaded test oracle)
+    const bool clipping = (flags & 2) != 0;
 
     for (uint32_t meshIdx = 0; meshIdx < count; meshIdx++) {
         if (orc_shade_meshlet(meshlets + meshletOffset, meshIdx, cullBitmap, objectToClip, materials, &mesh) == 0) continue;
         counters[0] += mesh.PrimCount;                                                     // :545
 
-        for (uint32_t prim = 0; prim < mesh.PrimCount; prim++) {                           // lanes of :550-594
-            Vec4 v[3];
-            for (int k = 0; k < 3; k++) {
-                uint32_t idx = mesh.Indices[k][prim] & 63;                                 // 64-entry permute (SIMD.h:219-230)
-                v[k] = { mesh.Position[0][idx], mesh.Position[1][idx], mesh.Position[2][idx], mesh.Position[3][idx] };
-            }
-            int cc = clip_codes(v, bx, by, nullptr);
-            if (cc & 2) counters[2] += 1;                                                  // :567-569
-            if (!(cc & 1)) continue;
-            TriSetup t;
-            if (!tri_setup(v[0], v[1], v[2], halfW, halfH, mesh.CullMode, t)) continue;    // :574-577
-            counters[1] += 1;                                                              // :579
-
+        const swr_meshlet& src = meshlets[meshletOffset + meshIdx];
+        const bool alpha = mesh.FragmentShaderId == 1 && textures != nullptr;              // Rasterizer.cpp:729 (DrawTriangle[FragmentShaderId])
+        const swr_material* mat = alpha ? &materials[src.MaterialId] : nullptr;
+        auto draw = [&](const TriSetup& t, uint32_t prim, const float* clipU, const float* clipV) {
             uint32_t bbMin, bbMax;
             render_bbox(t, halfW, halfH, bbMin, bbMax);                                    // :588 / :714
             TriEdges e;
             edge_setup(t, halfW, halfH, e);                                                // :721
             uint32_t surfaceId = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;         // Shading.cpp:328
-            if (mesh.FragmentShaderId == 1 && textures != nullptr) {                       // Rasterizer.cpp:729 (DrawTriangle[FragmentShaderId])
-                const swr_meshlet& src = meshlets[meshletOffset + meshIdx];
-                const swr_material& mat = materials[src.MaterialId];
+            if (alpha) {
                 uint32_t tc[3] = { src.TexCoords[mesh.Indices[0][prim] & 63], src.TexCoords[mesh.Indices[1][prim] & 63],
                                    src.TexCoords[mesh.Indices[2][prim] & 63] };
-                draw_triangle_alpha(color, depth, width, e, bbMin, bbMax, surfaceId, tc, &textures[mat.TextureId], mat.AlphaCutoff);
+                draw_triangle_alpha(color, depth, width, e, bbMin, bbMax, surfaceId, tc, &textures[mat->TextureId], mat->AlphaCutoff, clipU, clipV);
             } else {
                 draw_triangle(color, depth, width, e, bbMin, bbMax, surfaceId);
+            }
+        };
+
+        // 16-wide packets like the reference: a packet's accepted lanes are drawn first, then its clipped ones
+        // (Rasterizer.cpp:181-249) — the order only matters for exact depth ties.
+        for (uint32_t primOffset = 0; primOffset < mesh.PrimCount; primOffset += 16) {
+            uint32_t end = primOffset + 16 < mesh.PrimCount ? primOffset + 16 : mesh.PrimCount;
+            uint8_t outcodes[16];
+            int codes[16];
+            Vec4 pv[16][3];
+            for (uint32_t prim = primOffset; prim < end; prim++) {                         // lanes of :550-594
+                Vec4* v = pv[prim - primOffset];
+                for (int k = 0; k < 3; k++) {
+                    uint32_t idx = mesh.Indices[k][prim] & 63;                             // 64-entry permute (SIMD.h:219-230)
+                    v[k] = { mesh.Position[0][idx], mesh.Position[1][idx], mesh.Position[2][idx], mesh.Position[3][idx] };
+                }
+                int cc = codes[prim - primOffset] = clip_codes(v, bx, by, &outcodes[prim - primOffset]);
+                if ((cc & 2) && (clipping || !(flags & 4))) counters[2] += 1;              // :567-569 binned, :210 unbinned
+                if (!(cc & 1)) continue;
+                TriSetup t;
+                if (!tri_setup(v[0], v[1], v[2], halfW, halfH, mesh.CullMode, t)) continue;    // :574-577
+                counters[1] += 1;                                                          // :579
+                draw(t, prim, nullptr, nullptr);
+            }
+            if (!clipping) continue;
+            for (uint32_t prim = primOffset; prim < end; prim++) {                         // Rasterizer.cpp:209-249
+                if (!(codes[prim - primOffset] & 2)) continue;
+                Vec4 tris[7][3];
+                float remapU[7][3], remapV[7][3];
+                int n = clip_triangle(pv[prim - primOffset], outcodes[prim - primOffset], bx, by, tris, remapU, remapV);
+                for (int j = 0; j < n; j++) {
+                    TriSetup t;
+                    if (!tri_setup(tris[j][0], tris[j][1], tris[j][2], halfW, halfH, mesh.CullMode, t)) continue;   // FlushPacket :487
+                    counters[1] += 1;                                                      // :247
+                    draw(t, prim, remapU[j], remapV[j]);
+                }
             }
         }
     }

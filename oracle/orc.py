@@ -61,11 +61,13 @@ class Framebuffer:
 
 
 def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, count: int, object_to_clip,
-                  cull_bitmap=None, materials=None, guardband: bool = True, counters=None, textures=None) -> np.ndarray:
+                  cull_bitmap=None, materials=None, guardband: bool = True, counters=None, textures=None,
+                  binned: bool = True, clipping: bool = False) -> np.ndarray:
     """Rasterizer::DrawMeshlets + VisBufferShader on the CPU. Returns the 4 integer perf counters.
 
     With `textures`, alpha-tested materials (AlphaCutoff < 255) run FS_EncodeSurfaceId<true>; without, every
-    triangle takes the opaque program."""
+    triangle takes the opaque program. binned=False selects DrawMeshletsST's treatment of non-trivial triangles:
+    clipped and drawn with `clipping`, else dropped without being counted."""
     assert meshlets.dtype.itemsize == 1728
     if counters is None:
         counters = np.zeros(4, dtype=np.uint64)
@@ -75,7 +77,7 @@ def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, co
     descs, keep = (None, None) if not textures else _texture_descs(textures)
     lib().orc_draw_meshlets_ex(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
                                C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats, descs,
-                               C.c_uint32(1 if guardband else 0), _p(counters))
+                               C.c_uint32((1 if guardband else 0) | (0 if binned else (2 if clipping else 4))), _p(counters))
     return counters
 
 

@@ -28,11 +28,19 @@ CASES = {
     "c1_knot_960x540": lambda: (scenes.torus_knot_scene(120, 48, 960, 540, tex_size=64), False),
     "c3_odd_size_1000x564": lambda: (scenes.grid_scene(16, 12, 1000, 564, seed=8), False),
     "room_big_tris_1920x1080": lambda: (scenes.room_scene(), False),
+    "room_clipped_1920x1080": lambda: (scenes.room_scene(), False),
+    "knot_alpha_closeup_clipped_960x540": lambda: (scenes.closeup_alpha_scene(), False),
+}
+# Oracle mode per case (default: the binned path, non-trivial triangles counted and dropped). The *_clipped cases
+# pin the unbinned path with EnableClipping (Clipper::ClipTriangles, Rasterizer.cpp:398-491).
+MODES = {
+    "room_clipped_1920x1080": dict(binned=False, clipping=True),
+    "knot_alpha_closeup_clipped_960x540": dict(binned=False, clipping=True),
 }
 
 
-def digest(scene, cull):
-    fb, counters = oracle_render(orc, scene, cull=cull)
+def digest(scene, cull, **mode):
+    fb, counters = oracle_render(orc, scene, cull=cull, **mode)
     n = scene.width * scene.height
     return {"depth_sha256": hashlib.sha256(fb.data[1, :n].tobytes()).hexdigest(),
             "id_sha256": hashlib.sha256(fb.data[0, :n].tobytes()).hexdigest(),
@@ -41,7 +49,7 @@ def digest(scene, cull):
 
 
 if __name__ == "__main__":
-    out = {name: digest(*make()) for name, make in CASES.items()}
+    out = {name: digest(*make(), **MODES.get(name, {})) for name, make in CASES.items()}
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "visbuffer_hashes.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1))

@@ -2,8 +2,9 @@
 import numpy as np
 
 
-def oracle_render(orc, scene, cull=False, clear=(0xFF000000, 0.0), fb=None):
-    """Frame loop of Main.cpp:213-240 on the CPU oracle. Returns (fb, counters)."""
+def oracle_render(orc, scene, cull=False, clear=(0xFF000000, 0.0), fb=None, binned=True, clipping=False):
+    """Frame loop of Main.cpp:213-240 on the CPU oracle. Returns (fb, counters).
+    binned=False: DrawMeshletsST's handling of non-trivial triangles (clipped with `clipping`, else dropped uncounted)."""
     if fb is None:
         fb = orc.Framebuffer(scene.width, scene.height)
         fb.clear(*clear)
@@ -16,8 +17,14 @@ def oracle_render(orc, scene, cull=False, clear=(0xFF000000, 0.0), fb=None):
             bitmap, _ = orc.cull_meshlets(scene.meshlets[node.meshlet_offset:node.meshlet_offset + node.meshlet_count], planes)
         orc.draw_meshlets(fb, scene.meshlets, node.meshlet_offset, node.meshlet_count, scene.object_to_clip(node),
                           cull_bitmap=bitmap, materials=scene.materials, counters=counters,
-                          textures=scene.textures if len(scene.textures) else None)
+                          textures=scene.textures if len(scene.textures) else None, binned=binned, clipping=clipping)
     return fb, counters
+
+
+def raster_mode(rast):
+    """(binned, clipping) keyword arguments for the oracle that match a Rasterizer mirror's flags."""
+    from glimpsw_b200 import api
+    return dict(binned=bool(rast.flags & api.FLAG_BINNING), clipping=bool(rast.flags & api.FLAG_CLIPPING))
 
 
 def gpu_render(rast, scene, cull=False, clear=(0xFF000000, 0.0), batch=True, gscene=None, fb=None):

@@ -4,7 +4,7 @@ import pytest
 
 from glimpsw_b200 import scenes, camera as cam
 from glimpsw_b200.layout import MATERIAL_DTYPE
-from helpers import oracle_render, gpu_render, assert_visbuffer_equal
+from helpers import oracle_render, gpu_render, assert_visbuffer_equal, raster_mode
 from test_oracle_kat import meshlet_from_clip_tris, tri_px, fixed_to_ndc, IDENT
 
 pytestmark = pytest.mark.gpu
@@ -14,7 +14,7 @@ MODES = pytest.mark.parametrize("binning", [True, False], ids=["binned", "direct
 def compare(orc, rast, meshlets, w, h, materials=None, clear=(0xFFFFFFFF, 0.0)):
     ofb = orc.Framebuffer(w, h)
     ofb.clear(*clear)
-    oc = orc.draw_meshlets(ofb, meshlets, 0, len(meshlets), IDENT, materials=materials)
+    oc = orc.draw_meshlets(ofb, meshlets, 0, len(meshlets), IDENT, materials=materials, **raster_mode(rast))
     gscene = rast.upload_scene(meshlets, materials)
     gfb = rast.create_framebuffer(w, h)
     gfb.clear(*clear)
@@ -56,16 +56,17 @@ def test_guard_band_giants_and_int32_wrap(orc, rast_factory, binning):
             [(-1.5, 2.6, 0.5), (1.5, 2.67, 0.5), (1.5, -2.67, 0.6)],
             [(-1.49, -2.67, 0.2), (-1.49, 2.67, 0.7), (1.507, 0.0, 0.4)],
             [(-0.9, -0.9, 0.8), (-0.9, 0.9, 0.8), (0.9, -0.9, 0.1)],
-            [(1.6, -0.5, 0.5), (0.2, 0.5, 0.5), (0.2, -0.5, 0.5)]]      # beyond the guard band -> dropped
+            [(1.6, -0.5, 0.5), (0.2, 0.5, 0.5), (0.2, -0.5, 0.5)]]      # beyond the guard band -> dropped (binned) / clipped (direct)
     compare(orc, rast, meshlet_from_clip_tris(tris, material_id=0), w, h, materials=mats)
 
 
 @MODES
 def test_room_big_triangles_and_clipped_count(orc, rast_factory, binning):
     scene = scenes.room_scene()
-    ofb, oc = oracle_render(orc, scene)
+    rast = rast_factory(enable_binning=binning)
+    ofb, oc = oracle_render(orc, scene, **raster_mode(rast))      # direct mode: EnableClipping -> the crossers are clipped and drawn
     assert int(oc[2]) > 0            # the scene does contain guard-band / near-plane crossers
-    gfb, gc, _ = gpu_render(rast_factory(enable_binning=binning), scene)
+    gfb, gc, _ = gpu_render(rast, scene)
     assert_visbuffer_equal(ofb, gfb, "room")
     assert [gc["TrianglesProcessed"], gc["TrianglesRasterized"], gc["TrianglesClipped"]] == [int(oc[0]), int(oc[1]), int(oc[2])]
 
