@@ -116,8 +116,8 @@ SWRB_API int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, vo
 
 /* ---- hot path ------------------------------------------------------------------------ */
 /* ShadingContext::CullMeshlets frustum part (Shading.cpp:775-809, :865-867). Planes are
- * derived on the host from P,V,M exactly as the reference does; depth_pyramid must be NULL
- * (HiZ is a later row). Writes 1 bit/meshlet to bitmap_out_host (if non-NULL, ceil(count/16)
+ * derived on the host from P,V,M exactly as the reference does (the HiZ half is
+ * swrb_cull_meshlets_hiz below). Writes 1 bit/meshlet to bitmap_out_host (if non-NULL, ceil(count/16)
  * uint16) and keeps a device copy for UseDeviceCullBitmap. Returns the visible count. */
 SWRB_API int swrb_cull_meshlets(swrb_scene* scene, uint32_t meshlet_offset, uint32_t count,
                                 const float proj[16], const float view[16], const float model[16],
