@@ -1007,6 +1007,8 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     memcpy(rp.viewPos, u->ViewPos, sizeof(rp.viewPos));
     rp.exposure = u->Exposure;
     rp.width = fb->width; rp.height = fb->height;
+    rp.pixScaleX = 2.0f / (float)fb->width; rp.pixScaleY = 2.0f / (float)fb->height;
+    rp.pixBiasX = 0.5f * rp.pixScaleX - 1.0f; rp.pixBiasY = 0.5f * rp.pixScaleY - 1.0f;
     rp.meshlets = scene->meshlets; rp.materials = scene->materials; rp.textures = scene->textures;
     rp.lights = scene->lights; rp.numLights = scene->numLights; rp.numMeshlets = scene->numMeshlets;
     rp.color = fb->data; rp.depth = fb->data + fb->layerStride;
