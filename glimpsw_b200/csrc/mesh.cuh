@@ -61,19 +61,29 @@ __device__ __forceinline__ void count_single_tile(uint32_t* tileCount, bool acti
 __device__ __forceinline__ void raster_inline(const TriRecord& t, const BBox& r, const FrameParams& fp, unsigned long long* keys) {
     Edges e;
     edge_setup(t, fp.halfW, fp.halfH, e);
-    uint32_t rowE0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)r.minX + (uint32_t)e.b12 * (uint32_t)r.minY;
-    uint32_t rowE1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)r.minX + (uint32_t)e.b20 * (uint32_t)r.minY;
-    uint32_t rowE2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)r.minX + (uint32_t)e.b01 * (uint32_t)r.minY;
-    for (int32_t y = r.minY; y < r.maxY; y++) {
-        uint32_t e0 = rowE0, e1 = rowE1, e2 = rowE2;
-        for (int32_t x = r.minX; x < r.maxX; x++) {
-            if ((int32_t)(e0 | e1 | e2) >= 0) {                                   // Rasterizer.h:289-290
-                float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);               // :296
-                if (d > 0.0f) atomicMax(keys + fb_pixel_offset((uint32_t)x, (uint32_t)y, fp.width), make_key(d, t.id));
-            }
-            e0 += (uint32_t)e.a12; e1 += (uint32_t)e.a20; e2 += (uint32_t)e.a01;
+    uint32_t e0 = (uint32_t)e.e0 + (uint32_t)e.a12 * (uint32_t)r.minX + (uint32_t)e.b12 * (uint32_t)r.minY;
+    uint32_t e1 = (uint32_t)e.e1 + (uint32_t)e.a20 * (uint32_t)r.minX + (uint32_t)e.b20 * (uint32_t)r.minY;
+    uint32_t e2 = (uint32_t)e.e2 + (uint32_t)e.a01 * (uint32_t)r.minX + (uint32_t)e.b01 * (uint32_t)r.minY;
+    // One flat loop over the region's pixels instead of nested row/column loops: the lanes of a warp walk regions
+    // of different shapes, and a flat loop costs max(area) iterations per warp where nested loops cost
+    // sum over rows of max(width). The edge values step by A inside a row and by B - (w-1)*A at the row's end,
+    // all in wrapping 32-bit arithmetic — the same values the reference's incremental adds produce.
+    const int32_t w = r.maxX - r.minX, n = w * (r.maxY - r.minY);
+    const uint32_t wrap0 = (uint32_t)e.b12 - (uint32_t)(w - 1) * (uint32_t)e.a12;
+    const uint32_t wrap1 = (uint32_t)e.b20 - (uint32_t)(w - 1) * (uint32_t)e.a20;
+    const uint32_t wrap2 = (uint32_t)e.b01 - (uint32_t)(w - 1) * (uint32_t)e.a01;
+    int32_t x = r.minX, y = r.minY;
+    for (int32_t i = 0; i < n; i++) {
+        if ((int32_t)(e0 | e1 | e2) >= 0) {                                       // Rasterizer.h:289-290
+            float d = pixel_depth(e, (int32_t)e1, (int32_t)e2);                   // :296
+            if (d > 0.0f) atomicMax(keys + fb_pixel_offset((uint32_t)x, (uint32_t)y, fp.width), make_key(d, t.id));
         }
-        rowE0 += (uint32_t)e.b12; rowE1 += (uint32_t)e.b20; rowE2 += (uint32_t)e.b01;
+        const bool rowEnd = x + 1 == r.maxX;
+        e0 += rowEnd ? wrap0 : (uint32_t)e.a12;
+        e1 += rowEnd ? wrap1 : (uint32_t)e.a20;
+        e2 += rowEnd ? wrap2 : (uint32_t)e.a01;
+        x = rowEnd ? r.minX : x + 1;
+        y += rowEnd ? 1 : 0;
     }
 }
 
