@@ -130,6 +130,7 @@ struct swrb_scene {
     std::vector<uint32_t*> textureData;
     uint32_t numTextures = 0;
     swr_light* lights = nullptr;
+    std::vector<swr_light> lightsHost;    // for the light markers of Resolve (projected on the host)
     uint32_t numLights = 0;
     bool hasAlphaTest = false;
 };
@@ -351,6 +352,7 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     if (num_lights) {
         CU(cudaMalloc(&s->lights, num_lights * sizeof(swr_light)));
         CU(cudaMemcpyAsync(s->lights, lights, num_lights * sizeof(swr_light), cudaMemcpyHostToDevice, d->stream));
+        s->lightsHost.assign(lights, lights + num_lights);
     }
     CU(cudaStreamSynchronize(d->stream));   // host inputs are only borrowed for the duration of the call
     *out = s;
@@ -1018,6 +1020,28 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
         dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
         if (fromKeys) k_resolve<true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
         else k_resolve<false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        d->launches++;
+    }
+    // Tail of Resolve (Shading.cpp:690-731): point / spot lights inside the frustum become soft discs, in light order.
+    for (const swr_light& light : scene->lightsHost) {
+        if (light.Type == 0) continue;
+        const float* m = u->WorldToClip;
+        float clip[4];
+        for (int r = 0; r < 4; r++)     // glm mat4 * vec4: (m0*x + m1*y) + (m2*z + m3*w)
+            clip[r] = (m[0 * 4 + r] * light.Position[0] + m[1 * 4 + r] * light.Position[1]) + (m[2 * 4 + r] * light.Position[2] + m[3 * 4 + r] * 1.0f);
+        if (fmaxf(fmaxf(fabsf(clip[0]), fabsf(clip[1])), fabsf(clip[2])) > clip[3]) continue;
+        LightDisc ld;
+        ld.depth = clip[2] / clip[3];
+        const float sx = (clip[0] / clip[3]) * 0.5f + 0.5f, sy = (clip[1] / clip[3]) * 0.5f + 0.5f;
+        ld.radius = ((float)std::max(fb->width, fb->height) / 30.0f) / clip[3];
+        ld.cx = sx * (float)fb->width; ld.cy = sy * (float)fb->height;
+        ld.startX = std::max((int32_t)(ld.cx - ld.radius), 0) & ~3; ld.startY = std::max((int32_t)(ld.cy - ld.radius), 0) & ~3;
+        ld.endX = std::min((int32_t)(ld.cx + ld.radius), (int32_t)fb->width); ld.endY = std::min((int32_t)(ld.cy + ld.radius), (int32_t)fb->height);
+        memcpy(ld.color, light.Color, sizeof(ld.color));
+        if (ld.startX >= ld.endX || ld.startY >= ld.endY) continue;
+        StageScope ss(d, SWRB_STAGE_RESOLVE);
+        dim3 grid((uint32_t)(((ld.endX + 3) & ~3) - ld.startX + 31) / 32, (uint32_t)(((ld.endY + 3) & ~3) - ld.startY + 7) / 8);
+        k_light_marker<<<grid, dim3(32, 8), 0, d->stream>>>(ld, fb->data, fb->data + fb->layerStride, fromKeys ? fb->keys : nullptr, fb->width, d->ctl);
         d->launches++;
     }
     if (fromKeys) fb->layer0IsColor = true;      // depth is still only in the keys

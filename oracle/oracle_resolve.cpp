@@ -441,6 +441,51 @@ void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t h
                      objectToWorld3, invScreenProj, viewPos, exposure, 0, height);
 }
 
+// Tail of ShadingContext::Resolve (Shading.cpp:690-731): every point/spot light inside the frustum is drawn as a
+// soft disc over the resolved colour where it is not occluded (light depth > stored depth), lights in order.
+// glm's mat4 * vec4 is (m0*x + m1*y) + (m2*z + m3*w); vec / scalar is a true division. The reference skips 4x4
+// tiles without a pixel inside the disc; pixels outside the disc blend with alpha <= 0 -> 0, which AlphaBlendU8
+// (:239-246) leaves unchanged (|fg - bg| * 64 / 32768 rounds to 0), so the pass is written per pixel.
+void orc_draw_light_markers(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                            const swr_light* lights, uint32_t numLights, const float* worldToClip) {
+    const float* m = worldToClip;
+    for (uint32_t li = 0; li < numLights; li++) {
+        const swr_light& light = lights[li];
+        if (light.Type == 0) continue;                                                          // :693
+        float clip[4];
+        for (int r = 0; r < 4; r++)
+            clip[r] = (m[0 * 4 + r] * light.Position[0] + m[1 * 4 + r] * light.Position[1]) + (m[2 * 4 + r] * light.Position[2] + m[3 * 4 + r] * 1.0f);
+        if (std::fmax(std::fmax(std::fabs(clip[0]), std::fabs(clip[1])), std::fabs(clip[2])) > clip[3]) continue;   // :696
+        float lightDepth = clip[2] / clip[3];
+        float sx = (clip[0] / clip[3]) * 0.5f + 0.5f, sy = (clip[1] / clip[3]) * 0.5f + 0.5f;   // :699-701
+        float radius = ((float)(width > height ? width : height) / 30.0f) / clip[3];            // :702
+        float cx = sx * (float)width, cy = sy * (float)height;                                  // :704
+        int32_t startX = (int32_t)(cx - radius), startY = (int32_t)(cy - radius);               // int2() truncates
+        startX = (startX > 0 ? startX : 0) & ~3; startY = (startY > 0 ? startY : 0) & ~3;       // :705
+        int32_t endX = (int32_t)(cx + radius), endY = (int32_t)(cy + radius);
+        endX = endX < (int32_t)width ? endX : (int32_t)width; endY = endY < (int32_t)height ? endY : (int32_t)height;   // :706
+        for (int32_t ty = startY; ty < endY; ty += 4) {
+            for (int32_t tx = startX; tx < endX; tx += 4) {
+                for (int i = 0; i < 16; i++) {
+                    uint32_t x = (uint32_t)tx + (i & 3), y = (uint32_t)ty + (i >> 2);
+                    uint32_t off = ((x & ~3u) << 2) + (y & ~3u) * width + (x & 3) + (y & 3) * 4;
+                    if (!(lightDepth > depth[off])) continue;                                   // :712, :728
+                    float rx = ((float)(int32_t)x + 0.5f) - cx, ry = ((float)(int32_t)y + 0.5f) - cy;   // :715
+                    float distSq = std::fmaf(rx, rx, ry * ry) - radius * radius;                // :716
+                    float a = 1.0f - (-distSq / (radius * radius));                             // :724
+                    uint32_t fg = pack_rgba8(light.Color[0], light.Color[1], light.Color[2], 1.0f - a * a);
+                    uint32_t bg = color[off];
+                    uint32_t t = (fg >> 1) & 0x7F800000u;                                       // AlphaBlendU8 :239-246
+                    t |= (t >> 16) | 0x00400040u;
+                    uint32_t rb = lerp16(bg & 0x00FF00FFu, fg & 0x00FF00FFu, t);
+                    uint32_t ag = lerp16((bg >> 8) & 0x00FF00FFu, (fg >> 8) & 0x00FF00FFu, t);
+                    color[off] = rb | (ag << 8);
+                }
+            }
+        }
+    }
+}
+
 // Texture2D::SampleImplicitLod<SurfaceSampler>(u, v, layer 0) over one 4x4 fragment (Texture.h:403-410):
 // LOD from 2x2 finite differences inside the fragment (dFdx/dFdy, :260-269), CalcMipLevel(grad) - LerpFracBits
 // (:271-275, :408), fragment-wide filter vote in SampleLevel (:432). Used by the alpha-tested fragment program.

@@ -103,8 +103,9 @@ def _texture_descs(textures):
 
 
 def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, object_to_clip, object_to_world3,
-            inv_screen_proj, view_pos, exposure: float = 1.0, **_unused):
-    """ShadingContext::Resolve on the CPU: layer 0 (surface ids) is overwritten with RGBA8 colour."""
+            inv_screen_proj, view_pos, exposure: float = 1.0, world_to_clip=None, **_unused):
+    """ShadingContext::Resolve on the CPU: layer 0 (surface ids) is overwritten with RGBA8 colour; with
+    `world_to_clip`, point/spot lights are then drawn as markers like the tail of Resolve (Shading.cpp:690-731)."""
     assert meshlets.dtype.itemsize == 1728
     descs, keep = _texture_descs(textures)
     vp = np.ascontiguousarray(np.asarray(view_pos, dtype=np.float32))
@@ -114,6 +115,14 @@ def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, 
                       _p(materials) if len(materials) else None, descs, _p(lights) if len(lights) else None,
                       C.c_uint32(len(lights)), _p(_mat(object_to_clip)), _p(o2w), _p(_mat(inv_screen_proj)), _p(vp),
                       C.c_float(exposure))
+    if world_to_clip is not None and len(lights):
+        draw_light_markers(fb, lights, world_to_clip)
+
+
+def draw_light_markers(fb: Framebuffer, lights, world_to_clip) -> None:
+    lights = np.ascontiguousarray(lights)
+    lib().orc_draw_light_markers(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(lights),
+                                 C.c_uint32(len(lights)), _p(_mat(world_to_clip)))
 
 
 def generate_mip(tex, layer: int, level: int):
@@ -149,7 +158,7 @@ class Baseline:
         return counters
 
     def resolve(self, fb: Framebuffer, meshlets, materials, textures, lights, object_to_clip, object_to_world3,
-                inv_screen_proj, view_pos, exposure: float = 1.0, **_unused):
+                inv_screen_proj, view_pos, exposure: float = 1.0, world_to_clip=None, **_unused):
         descs, keep = _texture_descs(textures)
         vp = np.ascontiguousarray(np.asarray(view_pos, dtype=np.float32))
         o2w = np.ascontiguousarray(np.asarray(object_to_world3, dtype=np.float32).reshape(9))
@@ -158,6 +167,8 @@ class Baseline:
                              _p(meshlets), _p(materials) if len(materials) else None, descs,
                              _p(lights) if len(lights) else None, C.c_uint32(len(lights)), _p(_mat(object_to_clip)),
                              _p(o2w), _p(_mat(inv_screen_proj)), _p(vp), C.c_float(exposure))
+        if world_to_clip is not None and len(lights):
+            draw_light_markers(fb, lights, world_to_clip)
 
     def close(self):
         if self._h:
