@@ -142,7 +142,7 @@ def run_ours(args):
     # default stream has handle 0, which swrb_device_set_stream reads as "use your own stream").
     ctxs = []
     for i in range(F):
-        r = api.Rasterizer(local_rank, enable_binning=(args.mode == "binned"))
+        r = api.Rasterizer(local_rank, enable_binning=(args.mode == "binned"), resolve_cache=not args.no_resolve_cache)
         st = torch.cuda.Stream()
         assert st.cuda_stream != 0
         r.set_stream(st.cuda_stream)
@@ -491,6 +491,7 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resolve-cache", action="store_true", help="A/B switch: resolve re-transforms every pixel's corners (SWRB_FLAG_NO_RESOLVE_CACHE)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,6 +31,7 @@ FLAG_BINNING = 1 << 0
 FLAG_CLIPPING = 1 << 1
 FLAG_GUARDBAND = 1 << 2
 FLAG_FUSED_FRUSTUM_CULL = 1 << 3
+FLAG_NO_RESOLVE_CACHE = 1 << 4
 FLAGS_DEFAULT = FLAG_BINNING | FLAG_CLIPPING | FLAG_GUARDBAND
 
 PERF_NAMES = ["TrianglesProcessed", "TrianglesRasterized", "TrianglesClipped", "BinQueueFlushes",
@@ -85,10 +86,11 @@ def load_library() -> C.CDLL:
     """Loads libswrb.so. No fallback: a missing library is an error."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise SwrbError(f"{LIB_PATH} is missing: build it with `python -m glimpsw_b200.build` "
+        path = os.environ.get("SWRB_LIB", LIB_PATH)      # developer A/B builds only; there is still no non-CUDA path
+        if not os.path.exists(path):
+            raise SwrbError(f"{path} is missing: build it with `python -m glimpsw_b200.build` "
                             "(nvcc, sm_100a). There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         lib.swrb_last_error.restype = C.c_char_p
         lib.swrb_version.restype = C.c_char_p
         lib.swrb_device_destroy.restype = None
@@ -261,18 +263,20 @@ class Rasterizer:
     """swr::Rasterizer (Rasterizer.h:202-340) bound to one CUDA device."""
 
     def __init__(self, cuda_device: int = 0, enable_binning: bool = True, enable_clipping: bool = True,
-                 enable_guardband: bool = True, fused_frustum_cull: bool = False):
+                 enable_guardband: bool = True, fused_frustum_cull: bool = False, resolve_cache: bool = True):
         self.lib = load_library()
         self._h = C.c_void_p()
         self._children = weakref.WeakSet()   # framebuffers / scenes must die before the device
         self._pinned = []
         _check(self.lib.swrb_device_create(C.c_int(cuda_device), C.byref(self._h)))
-        self.set_flags(enable_binning, enable_clipping, enable_guardband, fused_frustum_cull)
+        self.set_flags(enable_binning, enable_clipping, enable_guardband, fused_frustum_cull, resolve_cache)
 
     # Rasterizer::EnableBinning / EnableClipping / EnableGuardband (Rasterizer.h:206-208)
-    def set_flags(self, enable_binning=True, enable_clipping=True, enable_guardband=True, fused_frustum_cull=False):
+    def set_flags(self, enable_binning=True, enable_clipping=True, enable_guardband=True, fused_frustum_cull=False,
+                  resolve_cache=True):
         self.flags = ((FLAG_BINNING if enable_binning else 0) | (FLAG_CLIPPING if enable_clipping else 0) |
-                      (FLAG_GUARDBAND if enable_guardband else 0) | (FLAG_FUSED_FRUSTUM_CULL if fused_frustum_cull else 0))
+                      (FLAG_GUARDBAND if enable_guardband else 0) | (FLAG_FUSED_FRUSTUM_CULL if fused_frustum_cull else 0) |
+                      (0 if resolve_cache else FLAG_NO_RESOLVE_CACHE))
         _check(self.lib.swrb_device_set_flags(self._h, C.c_uint32(self.flags)))
 
     def set_stream(self, cuda_stream: int | None):

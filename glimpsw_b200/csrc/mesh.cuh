@@ -94,7 +94,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
              unsigned long long* __restrict__ keys,
              TriRecord* __restrict__ tris, TriRecord* __restrict__ alphaTris, TriRecordW* __restrict__ alphaW, uint32_t triCapacity,
              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ bigList, uint2* __restrict__ clipList,
-             DevCtl* __restrict__ ctl) {
+             float4* __restrict__ clipCache, DevCtl* __restrict__ ctl) {
     __shared__ MeshWarpSmem smem[kMeshWarps];
     MeshWarpSmem& s = smem[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -179,6 +179,8 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                 s.nx[v] = nx; s.ny[v] = ny; s.z[v] = nz; s.rw[v] = rw;
                 s.pos[v] = ((uint32_t)X & 0xFFFFu) | ((uint32_t)Y << 16);
                 s.flags[v] = f;
+                // per-vertex x/w, y/w, 1/w for this frame's resolve pass (IntersectTriangle re-derives exactly these)
+                if (clipCache != nullptr) clipCache[(size_t)(d.meshletOffset + meshIdx) * SWR_MAX_VERTICES + v] = make_float4(nx, ny, rw, nz);
             }
         }
         __syncwarp();

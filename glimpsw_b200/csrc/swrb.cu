@@ -113,6 +113,16 @@ struct swrb_device {
     uint32_t lastTriCount = 0;            // records written by the most recent draw the host has read back
     swrb_fb* lastFb = nullptr;            // target of the last draw (its lazy state is rolled back if that draw aborted)
     bool lastFbPendingClear = false;
+
+    // Per-vertex {x/w, y/w, 1/w, z/w} of the last batch, written by the mesh kernel for the resolve pass.
+    // swrb_resolve may read it only if every surface id in the framebuffer provably comes from that batch
+    // and the batch used the one matrix the resolve is handed (see clip_cache_usable).
+    float4* clipCache = nullptr;
+    uint64_t clipCacheCap = 0;            // in meshlets
+    swrb_fb* clipCacheFb = nullptr;       // framebuffer the last batch drew into (null = cache unusable)
+    const swr_meshlet* clipCacheMeshlets = nullptr;
+    bool clipCacheUniform = false;        // all draws of that batch shared one ObjectToClip
+    float clipCacheM[16] = {};
 };
 
 struct DeviceTexture {     // Texture2D<RGBA8u, TiledY8> (Texture.h:314-329)
@@ -129,6 +139,8 @@ struct swrb_scene {
     ResolveTexture* textures = nullptr;   // device table
     std::vector<uint32_t*> textureData;
     uint32_t numTextures = 0;
+    float4* attr = nullptr;               // resolve-pass attribute table (k_decode_attributes), 2 float4 per vertex
+    uint32_t attrDirtyLo = 0, attrDirtyHi = 0;   // meshlet range whose attributes must be (re)decoded before the next resolve
     swr_light* lights = nullptr;
     std::vector<swr_light> lightsHost;    // for the light markers of Resolve (projected on the host)
     uint32_t numLights = 0;
@@ -152,6 +164,7 @@ struct swrb_fb {
 // An aborted draw (device work list overflow) never touched the depth / id layers; every kernel after it
 // was predicated off by the sticky device flag. Drop its keys and restore the recorded clear, if any.
 static void rollback_aborted_draw(swrb_device* d) {
+    d->clipCacheFb = nullptr;
     if (!d->lastFb) return;
     d->lastFb->visInKeys = false;
     d->lastFb->layer0IsColor = false;
@@ -246,7 +259,7 @@ void swrb_device_destroy(swrb_device* d) {
     cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
-    cudaFree(d->detileScratch); cudaFree(d->l2Scratch);
+    cudaFree(d->detileScratch); cudaFree(d->clipCache); cudaFree(d->l2Scratch);
     cudaEventDestroy(d->timerBegin); cudaEventDestroy(d->timerEnd);
     if (d->st) {
         for (int s = 0; s < SWRB_STAGE_COUNT_; s++)
@@ -316,6 +329,7 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     swrb_scene* s = new swrb_scene();
     s->dev = d;
     s->numMeshlets = num_meshlets;
+    s->attrDirtyLo = 0; s->attrDirtyHi = num_meshlets;
     if (num_meshlets) {
         CU(cudaMalloc(&s->meshlets, (size_t)num_meshlets * sizeof(swr_meshlet)));
         CU(cudaMemcpyAsync(s->meshlets, meshlets, (size_t)num_meshlets * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
@@ -364,6 +378,11 @@ int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint3
     if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
     CU(cudaSetDevice(s->dev->cudaDevice));
     CU(cudaMemcpyAsync(s->meshlets + first, meshlets, (size_t)count * sizeof(swr_meshlet), cudaMemcpyHostToDevice, s->dev->stream));
+    if (count) {
+        if (s->attrDirtyLo >= s->attrDirtyHi) { s->attrDirtyLo = first; s->attrDirtyHi = first + count; }
+        else { s->attrDirtyLo = std::min(s->attrDirtyLo, first); s->attrDirtyHi = std::max(s->attrDirtyHi, first + count); }
+        if (s->dev->clipCacheMeshlets == s->meshlets) s->dev->clipCacheFb = nullptr;   // cached vertices belong to the old positions
+    }
     return SWRB_OK;
 }
 
@@ -371,7 +390,8 @@ void swrb_scene_destroy(swrb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->dev->cudaDevice);
     cudaStreamSynchronize(s->dev->stream);
-    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights);
+    if (s->dev->clipCacheMeshlets == s->meshlets) s->dev->clipCacheFb = nullptr;
+    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights); cudaFree(s->attr);
     for (uint32_t* p : s->textureData) cudaFree(p);
     delete s;
 }
@@ -397,6 +417,7 @@ void swrb_fb_destroy(swrb_fb* fb) {
     cudaSetDevice(fb->dev->cudaDevice);
     cudaStreamSynchronize(fb->dev->stream);
     if (fb->dev->lastFb == fb) fb->dev->lastFb = nullptr;
+    if (fb->dev->clipCacheFb == fb) fb->dev->clipCacheFb = nullptr;
     cudaFree(fb->data); cudaFree(fb->keys);
     delete fb;
 }
@@ -807,7 +828,8 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
 }
 
 static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
-                         const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws) {
+                         const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws,
+                         bool forResolve = true) {
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     if (numDraws == 0) return SWRB_OK;
@@ -882,6 +904,23 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     const uint32_t numVec = fb->width * fb->height / 4;
     uint32_t* depthLayer = fb->data + fb->layerStride;
 
+    // ---- per-vertex clip cache for the resolve pass (any batch overwrites it, so it always describes the last one)
+    float4* clipCache = nullptr;
+    d->clipCacheFb = nullptr;
+    if (forResolve && !(d->flags & SWRB_FLAG_NO_RESOLVE_CACHE)) {
+        if (numMeshletsDev > d->clipCacheCap) {
+            rc = ensure_buffer((void**)&d->clipCache, &d->clipCacheCap, numMeshletsDev, sizeof(float4) * SWR_MAX_VERTICES);
+            if (rc) return rc;
+        }
+        clipCache = d->clipCache;
+        d->clipCacheFb = fb;
+        d->clipCacheMeshlets = meshletsDev;
+        memcpy(d->clipCacheM, draws[0].ObjectToClip, sizeof(d->clipCacheM));
+        d->clipCacheUniform = true;
+        for (uint32_t i = 1; i < numDraws; i++)
+            if (memcmp(draws[i].ObjectToClip, d->clipCacheM, sizeof(d->clipCacheM)) != 0) d->clipCacheUniform = false;
+    }
+
     // ---- key buffer: seeds = the depth every pixel has before this draw (or the pending clear's depth)
     if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
     if (fb->visInKeys) {           // an earlier draw's result is still only in the keys: the layers must be current to re-seed
@@ -905,7 +944,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         {
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, nullptr, d->ctl);
+                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, nullptr, clipCache, d->ctl);
             d->launches++;
         }
         {
@@ -926,7 +965,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
             StageScope ss(d, SWRB_STAGE_MESH);
             k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
                                                                             d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr,
-                                                                            reinterpret_cast<uint2*>(d->binEntries), d->ctl);   // (the bin-entry buffer is idle on this path)
+                                                                            reinterpret_cast<uint2*>(d->binEntries), clipCache, d->ctl);   // (the bin-entry buffer is idle on this path)
             d->launches++;
             if (fp.clipMode == 2u) {       // Clipper::ClipTriangles: pieces join the record / alpha lists before they are consumed
                 k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, d->drawItems, fp,
@@ -988,7 +1027,7 @@ int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint3
     desc.MeshletCount = count;
     memcpy(desc.ObjectToClip, object_to_clip, sizeof(desc.ObjectToClip));
     desc.CullBitmapHost = cull_bitmap_host;
-    return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, nullptr, false, &desc, 1);
+    return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, nullptr, false, &desc, 1, /*forResolve=*/false);
 }
 
 // ---- resolve -----------------------------------------------------------------------------------
@@ -1013,13 +1052,33 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     rp.pixBiasX = 0.5f * rp.pixScaleX - 1.0f; rp.pixBiasY = 0.5f * rp.pixScaleY - 1.0f;
     rp.meshlets = scene->meshlets; rp.materials = scene->materials; rp.textures = scene->textures;
     rp.lights = scene->lights; rp.numLights = scene->numLights; rp.numMeshlets = scene->numMeshlets;
+    memset(rp.lightsInline, 0, sizeof(rp.lightsInline));
+    for (uint32_t i = 0; i < std::min<uint32_t>(kInlineLights, (uint32_t)scene->lightsHost.size()); i++) rp.lightsInline[i] = scene->lightsHost[i];
     rp.color = fb->data; rp.depth = fb->data + fb->layerStride;
     rp.keys = fb->keys; rp.keysClearMode = fb->keysClearMode ? 1u : 0u; rp.clearColor = fb->keysClearColor;
+    // attribute table: decode what changed since the last resolve (scene upload / swrb_scene_update_meshlets)
+    if (!scene->attr && scene->numMeshlets) CU(cudaMalloc(&scene->attr, (size_t)scene->numMeshlets * SWR_MAX_VERTICES * 2 * sizeof(float4)));
+    if (scene->attrDirtyLo < scene->attrDirtyHi) {
+        StageScope ss(d, SWRB_STAGE_RESOLVE);
+        const uint32_t count = scene->attrDirtyHi - scene->attrDirtyLo;
+        k_decode_attributes<<<(count * SWR_MAX_VERTICES + 255) / 256, 256, 0, d->stream>>>(scene->meshlets, scene->attrDirtyLo, count, scene->attr);
+        d->launches++;
+        scene->attrDirtyLo = scene->attrDirtyHi = 0;
+    }
+    rp.attr = scene->attr;
+    // The clip cache may stand in for the per-pixel corner transform only if every surface id the pass can meet
+    // was written by the last batch (vis-buffer still in that batch's keys, drawn from a cleared framebuffer whose
+    // clear depth marks sky), that batch used ONE matrix, and it is bit for bit the matrix of this resolve
+    // (ShadingContext::Resolve transforms with the context's current ObjectToClipMat, Shading.cpp:509-511).
+    const bool cached = fromKeys && fb->keysClearMode && fb->clearDepthBits == 0 && d->clipCacheFb == fb && d->clipCacheUniform &&
+                        d->clipCacheMeshlets == scene->meshlets && memcmp(d->clipCacheM, u->ObjectToClip, sizeof(d->clipCacheM)) == 0;
+    rp.clipCache = cached ? d->clipCache : nullptr;
     {
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
-        if (fromKeys) k_resolve<true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
-        else k_resolve<false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        if (cached) k_resolve<true, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        else if (fromKeys) k_resolve<true, false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        else k_resolve<false, false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
         d->launches++;
     }
     // Tail of Resolve (Shading.cpp:690-731): point / spot lights inside the frustum become soft discs, in light order.

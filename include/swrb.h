@@ -48,6 +48,10 @@ enum {
     SWRB_FLAG_GUARDBAND = 1u << 2,  /* EnableGuardband (ignored by the binned path, Rasterizer.cpp:509) */
     SWRB_FLAG_FUSED_FRUSTUM_CULL = 1u << 3, /* evaluate CullMeshlets' frustum test inside the mesh kernel
                                                (planes from swrb_draw_desc.FrustumPlanes) */
+    SWRB_FLAG_NO_RESOLVE_CACHE = 1u << 4,   /* the mesh kernel does not keep per-vertex x/w, y/w, 1/w for the resolve pass;
+                                               swrb_resolve then re-transforms every pixel's three corners itself
+                                               (same bits either way — saves 1 KB of writes per drawn meshlet for
+                                               callers that never resolve) */
     SWRB_FLAGS_DEFAULT = SWRB_FLAG_BINNING | SWRB_FLAG_CLIPPING | SWRB_FLAG_GUARDBAND
 };
 

@@ -69,3 +69,73 @@ def test_resolve_minified_and_magnified(orc, rast_factory):
     near.camera.position[:] = (0.2, 0.9, 2.6)
     (max_abs, psnr, _), _, _ = run_scene(orc, rast_factory(), near)
     assert max_abs <= MAX_ABS and psnr >= MIN_PSNR
+
+
+# ---- the resolve pass's per-vertex clip cache (k_resolve<.., kClipCached>) ------------------------------------------
+def _frame(rast, scene, gscene=None, per_node_calls=False, resolve_node=0, fb=None):
+    """clear -> draw -> resolve with NO read-back in between (a read-back unpacks the keys and takes the uncached path)."""
+    if gscene is None:
+        gscene = rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)
+    if fb is None:
+        fb = rast.create_framebuffer(scene.width, scene.height)
+    fb.clear(0xFF000000, 0.0)
+    draws = [dict(offset=n.meshlet_offset, count=n.meshlet_count, object_to_clip=scene.object_to_clip(n)) for n in scene.nodes]
+    if per_node_calls:
+        for d in draws:
+            rast.draw_meshlets(fb, gscene, d["offset"], d["count"], d["object_to_clip"])
+    else:
+        rast.draw_batch(fb, gscene, draws)
+    rast.resolve(fb, gscene, **scenes.resolve_uniforms(scene, scene.nodes[resolve_node]))
+    return fb, gscene
+
+
+@pytest.mark.parametrize("binning", [True, False], ids=["binned", "direct"])
+def test_resolve_clip_cache_is_bit_identical_and_in_tolerance(orc, rast_factory, binning):
+    scene = scenes.torus_knot_scene(120, 48, 1280, 720, tex_size=256, extra_lights=True)
+    cached, _ = _frame(rast_factory(enable_binning=binning), scene)
+    plain, _ = _frame(rast_factory(enable_binning=binning, resolve_cache=False), scene)
+    a, b = cached.download_tiled(0), plain.download_tiled(0)
+    assert np.array_equal(a, b), f"{int((a != b).sum())} pixels differ between the cached and the re-transforming resolve"
+    ofb, _ = oracle_render(orc, scene)
+    orc.resolve(ofb, scene.meshlets, scene.materials, scene.textures, scene.lights, **scenes.resolve_uniforms(scene, scene.nodes[0]))
+    max_abs, psnr, frac = color_error(ofb.data[0, :scene.width * scene.height], a)
+    assert max_abs <= MAX_ABS and psnr >= MIN_PSNR, f"max abs {max_abs}/255, PSNR {psnr:.1f} dB, {frac:.4%} pixels differ"
+    # the depth layer is still intact after a cached resolve (it is unpacked from the keys on demand)
+    assert np.array_equal(cached.download_tiled(1), ofb.data[1, :scene.width * scene.height])
+
+
+def test_resolve_clip_cache_falls_back_when_matrices_differ(rast_factory):
+    """ShadingContext::Resolve transforms every pixel with the context's CURRENT ObjectToClipMat (Shading.cpp:509-511),
+    also pixels of nodes drawn with another matrix; the cache must not change that."""
+    from glimpsw_b200 import textures as tx
+    from glimpsw_b200.layout import MATERIAL_DTYPE
+    scene = scenes.instanced_scene(subdivisions=3, instances=27, width=640, height=360)
+    scene.meshlets["MaterialId"] = 0
+    scene.materials = np.zeros(1, dtype=MATERIAL_DTYPE)
+    scene.materials["AlphaCutoff"] = 255
+    scene.textures = [tx.procedural_material_texture(128, seed=3)]
+    scene.lights = scenes.default_light()
+    for per_node in (False, True):
+        cached, _ = _frame(rast_factory(), scene, per_node_calls=per_node, resolve_node=1)
+        plain, _ = _frame(rast_factory(resolve_cache=False), scene, per_node_calls=per_node, resolve_node=1)
+        a, b = cached.download_tiled(0), plain.download_tiled(0)
+        assert (a != 0xFF000000).mean() > 0.02, "nothing was shaded"
+        assert np.array_equal(a, b)
+
+
+def test_resolve_after_meshlet_update_uses_new_positions(rast_factory):
+    scene = scenes.torus_knot_scene(60, 24, 640, 360, tex_size=128)
+    moved = scene.meshlets.copy()
+    moved["Positions"][:, 1, :] += 0.05
+    imgs = []
+    for cache in (True, False):
+        rast = rast_factory(resolve_cache=cache)
+        gscene = rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)
+        fb = rast.create_framebuffer(scene.width, scene.height)
+        fb.clear(0xFF000000, 0.0)
+        n = scene.nodes[0]
+        rast.draw_meshlets(fb, gscene, n.meshlet_offset, n.meshlet_count, scene.object_to_clip(n))
+        gscene.update_meshlets(moved, 0)           # between draw and resolve: the reference would shade the moved vertices
+        rast.resolve(fb, gscene, **scenes.resolve_uniforms(scene, n))
+        imgs.append(fb.download_tiled(0))
+    assert np.array_equal(imgs[0], imgs[1])
