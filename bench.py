@@ -127,6 +127,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, ...) is routed to stderr until the line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -395,6 +400,8 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.rast.destroy()

@@ -50,8 +50,12 @@ EXPORTS = [
     "swrb_device_enable_stage_timing", "swrb_get_stage_times", "swrb_get_launch_count",
     "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
     "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
-    "swrb_hiz_download", "swrb_cull_meshlets_hiz",
+    "swrb_hiz_download", "swrb_cull_meshlets_hiz", "swrb_draw_batch_program", "swrb_resolve_debug",
 ]
+
+PROGRAM_VISBUFFER, PROGRAM_OVERDRAW = 0, 1     # ShadingContext::VisBufferShader / OverdrawShader (Shading.h:49)
+# enum class DebugLayer (Shading.h:8)
+DEBUG_LAYERS = ["None", "BaseColor", "Normals", "MetallicRoughness", "MeshletId", "TriangleId", "OverdrawPixel", "OverdrawQuad"]
 
 
 class SwrbError(RuntimeError):
@@ -340,14 +344,18 @@ class Rasterizer:
         d = self._desc(meshlet_offset, count, object_to_clip, cull_bitmap, use_device_bitmap, planes, keep)
         _check(self.lib.swrb_draw_meshlets(fb._h, scene._h, C.byref(d)))
 
-    def draw_batch(self, fb: Framebuffer, scene: Scene, draws: list):
-        """draws: list of dicts(offset, count, object_to_clip[, cull_bitmap, use_device_bitmap, planes])."""
+    def draw_batch(self, fb: Framebuffer, scene: Scene, draws: list, program: int = PROGRAM_VISBUFFER):
+        """draws: list of dicts(offset, count, object_to_clip[, cull_bitmap, use_device_bitmap, planes]).
+        program: the shader table of the DrawMeshlets calls — PROGRAM_VISBUFFER, or PROGRAM_OVERDRAW (FS_Overdraw)."""
         keep = []
         arr = (DrawDesc * len(draws))()
         for i, dd in enumerate(draws):
             arr[i] = self._desc(dd["offset"], dd["count"], dd["object_to_clip"], dd.get("cull_bitmap"),
                                 dd.get("use_device_bitmap", False), dd.get("planes"), keep)
-        _check(self.lib.swrb_draw_batch(fb._h, scene._h, arr, C.c_uint32(len(draws))))
+        if program == PROGRAM_VISBUFFER:
+            _check(self.lib.swrb_draw_batch(fb._h, scene._h, arr, C.c_uint32(len(draws))))
+        else:
+            _check(self.lib.swrb_draw_batch_program(fb._h, scene._h, arr, C.c_uint32(len(draws)), C.c_uint32(program)))
 
     def make_batch(self, draws: list):
         """Pre-builds the descriptor array of draw_batch for repeated submission (bench loops)."""
@@ -384,6 +392,13 @@ class Rasterizer:
                 view_pos, exposure: float = 1.0):
         u = self.make_uniforms(world_to_clip, object_to_clip, object_to_world3, inv_screen_proj, view_pos, exposure)
         _check(self.lib.swrb_resolve(fb._h, scene._h, C.byref(u)))
+
+    # ShadingContext::ResolveDebug (Shading.cpp:734-773)
+    def resolve_debug(self, fb: Framebuffer, scene: Scene, layer, world_to_clip, object_to_clip, object_to_world3,
+                      inv_screen_proj, view_pos=(0.0, 0.0, 0.0), exposure: float = 1.0):
+        layer = DEBUG_LAYERS.index(layer) if isinstance(layer, str) else int(layer)
+        u = self.make_uniforms(world_to_clip, object_to_clip, object_to_world3, inv_screen_proj, view_pos, exposure)
+        _check(self.lib.swrb_resolve_debug(fb._h, scene._h, C.byref(u), C.c_uint32(layer)))
 
     def resolve_prebuilt(self, fb: Framebuffer, scene: Scene, uniforms: ShadingUniforms):
         _check(self.lib.swrb_resolve(fb._h, scene._h, C.byref(uniforms)))

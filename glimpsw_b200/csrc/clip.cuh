@@ -45,7 +45,7 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
         if (materialId != SWR_NO_MATERIAL && materials != nullptr) {
             swr_material mat = materials[materialId];
             cullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
-            fsId = mat.AlphaCutoff < 255 ? 1u : 0u;
+            fsId = (mat.AlphaCutoff < 255 && fp.program == 0u) ? 1u : 0u;
         }
 
         ClipVert verts[16];          // 3 + at most 2 new vertices per plane (Clipper::Vertices, nextIdx <= 64 there)

@@ -149,6 +149,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             cullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
             fsId = mat.AlphaCutoff < 255 ? 1u : 0u;
         }
+        if (fp.program != 0u) fsId = 0;                                         // one fragment program in every slot
         if (lane < 24) reinterpret_cast<uint4*>(s.idx)[lane] = idxWord;
 
         // ---- transform + per-vertex setup: lane owns vertices lane and lane+32
@@ -217,7 +218,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                         BBox r;
                         if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {     // else: counted, touches no pixel
                             const int32_t area = (r.maxX - r.minX) * (r.maxY - r.minY);
-                            if (fsId == 0 && area <= kInlineMaxArea) {
+                            if (fsId == 0 && area <= kInlineMaxArea && fp.program == 0u) {
                                 TriRecord t;
                                 t.pos0 = p0; t.pos1 = p1; t.pos2 = p2;
                                 t.z0 = s.z[i0]; t.z1 = s.z[i1]; t.z2 = s.z[i2];

@@ -27,6 +27,7 @@
 #include "resolve.cuh"
 #include "alpha.cuh"
 #include "clip.cuh"
+#include "overdraw.cuh"
 
 using namespace swrb;
 
@@ -814,6 +815,7 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
 
 static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool binned) {
     FrameParams fp;
+    fp.program = SWRB_PROGRAM_VISBUFFER;
     fp.width = fb->width; fp.height = fb->height;
     fp.halfW = (int32_t)fb->width / 2; fp.halfH = (int32_t)fb->height / 2;          // Rasterizer.cpp:508
     fp.fixX = (float)(fp.halfW * 16); fp.fixY = (float)(fp.halfH * 16);               // :272
@@ -829,10 +831,11 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
 
 static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
                          const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws,
-                         bool forResolve = true) {
+                         bool forResolve = true, uint32_t program = SWRB_PROGRAM_VISBUFFER) {
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     if (numDraws == 0) return SWRB_OK;
+    if (program > SWRB_PROGRAM_OVERDRAW) return fail(SWRB_E_INVALID, "unknown program %u", program);
     const bool binned = (d->flags & SWRB_FLAG_BINNING) != 0;
 
     // ---- per-draw items
@@ -903,6 +906,41 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t numVec = fb->width * fb->height / 4;
     uint32_t* depthLayer = fb->data + fb->layerStride;
+
+    // ---- OverdrawShader: no depth test, nothing to resolve lazily — straight into the layers
+    if (program == SWRB_PROGRAM_OVERDRAW) {
+        fp.program = program;
+        if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
+        rc = fb_materialize(fb);                // layers current (a recorded clear is executed now)
+        if (rc) return rc;
+        d->clipCacheFb = nullptr;
+        d->lastFb = nullptr;                    // (no lazy state to roll back: an aborted draw skips k_overdraw_finish)
+        {
+            StageScope ss(d, SWRB_STAGE_CLEAR);
+            k_overdraw_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), numVec, d->ctl);
+            d->launches++;
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_MESH);
+            k_mesh_setup<false><<<grid_for(d, totalWork, kMeshWarps, 4), kMeshWarps * 32, 0, d->stream>>>(
+                meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys, d->tris, d->alphaTris, d->trisW,
+                (uint32_t)d->triCap, nullptr, nullptr, reinterpret_cast<uint2*>(d->binEntries), nullptr, d->ctl);
+            d->launches++;
+            if (fp.clipMode == 2u) {
+                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, d->drawItems, fp,
+                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, (uint32_t)d->triCap, d->ctl);
+                d->launches++;
+            }
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_RASTER);
+            k_raster_overdraw<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, fp, fb->keys, depthLayer, d->ctl);
+            k_overdraw_finish<<<grid_for(d, (uint64_t)fb->width * fb->height, 256, 8), 256, 0, d->stream>>>(fb->keys, fb->data, fb->width * fb->height, d->ctl);
+            d->launches += 2;
+        }
+        CU(cudaGetLastError());
+        return SWRB_OK;
+    }
 
     // ---- per-vertex clip cache for the resolve pass (any batch overwrites it, so it always describes the last one)
     float4* clipCache = nullptr;
@@ -1005,6 +1043,13 @@ int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws,
     return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, draws, num_draws);
 }
 
+int swrb_draw_batch_program(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, uint32_t program) {
+    if (!fb || !scene || (!draws && num_draws)) return fail(SWRB_E_INVALID, "null argument");
+    if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
+    return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, draws, num_draws,
+                         true, program);
+}
+
 int swrb_draw_meshlets(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draw) {
     return swrb_draw_batch(fb, scene, draw, 1);
 }
@@ -1031,7 +1076,31 @@ int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint3
 }
 
 // ---- resolve -----------------------------------------------------------------------------------
+static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u, int debugLayer);
+
 int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u) {
+    return resolve_internal(fb, scene, u, SWRB_LAYER_NONE);
+}
+
+int swrb_resolve_debug(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u, uint32_t layer) {
+    if (layer < SWRB_LAYER_BASE_COLOR || layer > SWRB_LAYER_OVERDRAW_QUAD) return fail(SWRB_E_INVALID, "debug layer %u out of range [1, 7]", layer);
+    if (!fb || !scene || !u) return fail(SWRB_E_INVALID, "null argument");
+    if (layer <= SWRB_LAYER_METALLIC_ROUGHNESS) return resolve_internal(fb, scene, u, (int)layer);
+    // the remaining layers are functions of the colour word alone (Shading.cpp:755-766)
+    if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    int rc = fb_materialize(fb);
+    if (rc) return rc;
+    StageScope ss(d, SWRB_STAGE_RESOLVE);
+    dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
+    k_resolve_debug_ids<<<grid, dim3(32, 8), 0, d->stream>>>(fb->data, fb->data + fb->layerStride, fb->width, fb->height, (int)layer);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u, int debugLayer) {
     if (!fb || !scene || !u) return fail(SWRB_E_INVALID, "null argument");
     if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
     swrb_device* d = fb->dev;
@@ -1073,6 +1142,17 @@ int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u)
     const bool cached = fromKeys && fb->keysClearMode && fb->clearDepthBits == 0 && d->clipCacheFb == fb && d->clipCacheUniform &&
                         d->clipCacheMeshlets == scene->meshlets && memcmp(d->clipCacheM, u->ObjectToClip, sizeof(d->clipCacheM)) == 0;
     rp.clipCache = cached ? d->clipCache : nullptr;
+    rp.debugLayer = debugLayer;
+    if (debugLayer != SWRB_LAYER_NONE) {            // ResolveDebug: surface only, no lighting, no light markers
+        StageScope ss(d, SWRB_STAGE_RESOLVE);
+        dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
+        if (fromKeys) k_resolve<true, false, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        else k_resolve<false, false, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        d->launches++;
+        if (fromKeys) fb->layer0IsColor = true;
+        CU(cudaGetLastError());
+        return SWRB_OK;
+    }
     {
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);

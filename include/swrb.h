@@ -158,6 +158,28 @@ SWRB_API int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_ho
 /* ShadingContext::Resolve (Shading.cpp:658-689): overwrites layer 0 with RGBA8 colour. */
 SWRB_API int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* uniforms);
 
+/* The shader tables a DrawMeshlets call can be bound to (ShadingContext::VisBufferShader / OverdrawShader,
+ * Shading.h:49, Shading.cpp:648-656). DeferredShader is not offered: its fragment program FS_EncodeGBuffer is an
+ * empty function at this snapshot of the reference (Shading.cpp:344-346). */
+typedef enum swrb_program {
+    SWRB_PROGRAM_VISBUFFER = 0,   /* ShadeMeshlet + FS_EncodeSurfaceId<false/true> */
+    SWRB_PROGRAM_OVERDRAW  = 1    /* ShadeMeshlet + FS_Overdraw (Shading.cpp:333-342) in every fragment slot: layer 0 counts
+                                     covered pixels (high u16) and helper lanes of touched 4x4 fragments (low u16), saturating;
+                                     layer 1 keeps max(depth); no depth test */
+} swrb_program;
+/* Rasterizer::DrawMeshlets(fb, count, {table, &ctx}) with the table chosen by `program` (Main.cpp:204-209, :236-240). */
+SWRB_API int swrb_draw_batch_program(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, uint32_t program);
+
+/* enum class DebugLayer (Shading.h:8) */
+typedef enum swrb_debug_layer {
+    SWRB_LAYER_NONE = 0, SWRB_LAYER_BASE_COLOR, SWRB_LAYER_NORMALS, SWRB_LAYER_METALLIC_ROUGHNESS, SWRB_LAYER_MESHLET_ID,
+    SWRB_LAYER_TRIANGLE_ID, SWRB_LAYER_OVERDRAW_PIXEL, SWRB_LAYER_OVERDRAW_QUAD
+} swrb_debug_layer;
+/* ShadingContext::ResolveDebug (Shading.cpp:734-773): overwrites layer 0 with the visualisation of `layer`
+ * (the overdraw layers expect a framebuffer drawn with SWRB_PROGRAM_OVERDRAW). SWRB_LAYER_NONE is invalid here
+ * (the Playground calls Resolve instead, Main.cpp:248-252). */
+SWRB_API int swrb_resolve_debug(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* uniforms, uint32_t layer);
+
 /* ---- pinned host staging (cudaMallocHost) for callers that want full-rate PCIe copies ------ */
 SWRB_API int swrb_alloc_pinned(swrb_device* dev, uint64_t bytes, void** out);
 SWRB_API int swrb_free_pinned(swrb_device* dev, void* ptr);

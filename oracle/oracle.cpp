@@ -254,6 +254,38 @@ inline void draw_triangle(uint32_t* color, float* depth, uint32_t width, const T
     }
 }
 
+// Rasterizer::DrawTriangle<FS_Overdraw, *> — Rasterizer.h:250-328 + Shading.cpp:333-342. The fragment program runs
+// once per 4x4 fragment of the triangle's (4-aligned) bounding box that has at least one covered lane (:284), on
+// all 16 lanes (it sets TileMask = 0xFFFF): covered lanes add 1 to the high u16 of the colour word, the others
+// add 1 to the low u16, both saturating (_mm512_adds_epu16); the depth layer takes max(Depth, stored) on all 16
+// lanes, Depth being the plane equation extrapolated to lanes outside the triangle. No depth test.
+inline void draw_triangle_overdraw(uint32_t* color, float* depth, uint32_t width, const TriEdges& e, uint32_t bbMin, uint32_t bbMax) {
+    uint32_t minX = bbMin & 0xFFFF, minY = bbMin >> 16, maxX = bbMax & 0xFFFF, maxY = bbMax >> 16;
+    for (uint32_t fy = minY; fy < maxY; fy += 4) {
+        for (uint32_t fx = minX; fx < maxX; fx += 4) {
+            uint32_t e1v[16], e2v[16], mask = 0;
+            for (uint32_t lane = 0; lane < 16; lane++) {
+                uint32_t x = fx + (lane & 3), y = fy + (lane >> 2);                     // Rasterizer.h:247-248
+                uint32_t e0 = (uint32_t)e.Edge0 + (uint32_t)e.A12 * x + (uint32_t)e.B12 * y;
+                e1v[lane] = (uint32_t)e.Edge1 + (uint32_t)e.A20 * x + (uint32_t)e.B20 * y;
+                e2v[lane] = (uint32_t)e.Edge2 + (uint32_t)e.A01 * x + (uint32_t)e.B01 * y;
+                if ((int32_t)(e0 | e1v[lane] | e2v[lane]) >= 0) mask |= 1u << lane;
+            }
+            if (mask == 0) continue;                                                     // :284
+            for (uint32_t lane = 0; lane < 16; lane++) {
+                uint32_t off = fb_pixel_offset(fx + (lane & 3), fy + (lane >> 2), width);
+                uint32_t c = color[off], hi = c >> 16, lo = c & 0xFFFF;
+                if ((mask >> lane) & 1) hi = hi < 0xFFFF ? hi + 1 : 0xFFFF;              // Shading.cpp:336-337
+                else lo = lo < 0xFFFF ? lo + 1 : 0xFFFF;
+                color[off] = (hi << 16) | lo;
+                float u = (float)(int32_t)e1v[lane], v = (float)(int32_t)e2v[lane];
+                float d = std::fmaf(u, e.Z10, std::fmaf(v, e.Z20, e.Z0));                // Rasterizer.h:296
+                depth[off] = std::fmax(d, depth[off]);                                   // Shading.cpp:341
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // Texture2D::SampleImplicitLod<SurfaceSampler> over one 4x4 fragment (oracle_resolve.cpp).
@@ -444,7 +476,9 @@ void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_
             TriEdges e;
             edge_setup(t, halfW, halfH, e);                                                // :721
             uint32_t surfaceId = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;         // Shading.cpp:328
-            if (alpha) {
+            if (flags & 8) {                                                               // ShadingContext::OverdrawShader: every slot is FS_Overdraw (Shading.cpp:656)
+                draw_triangle_overdraw(color, depth, width, e, bbMin, bbMax);
+            } else if (alpha) {
                 uint32_t tc[3] = { src.TexCoords[mesh.Indices[0][prim] & 63], src.TexCoords[mesh.Indices[1][prim] & 63],
                                    src.TexCoords[mesh.Indices[2][prim] & 63] };
                 draw_triangle_alpha(color, depth, width, e, bbMin, bbMax, surfaceId, tc, &textures[mat->TextureId], mat->AlphaCutoff, clipU, clipV);

@@ -207,7 +207,34 @@ inline float light_attenuation(const swr_light& light, V3 p) {
 
 struct Surface { uint32_t albedo; V3 normal; float metallic, roughness; };
 
+// ColormapTurbo (Shading.cpp:249-260): three degree-5 polynomials in Horner form
+inline void colormap_turbo(float x, float out[3]) {
+    static const float c[] = {
+        0.13572138f, 4.61539260f,  -42.66032258f, 132.13108234f, -152.94239396f, 59.28637943f,
+        0.09140261f, 2.19418839f,  4.84296658f,   -14.18503333f, 4.27729857f,    2.82956604f,
+        0.10667330f, 12.64194608f, -60.58204836f, 110.36276771f, -89.90310912f,  27.34824973f,
+    };
+    for (int k = 0; k < 3; k++) {
+        const float* p = c + 6 * k;
+        out[k] = x * (x * (x * (x * (x * p[5] + p[4]) + p[3]) + p[2]) + p[1]) + p[0];
+    }
+}
+inline void unpack_rgba8(uint32_t p, float out[3]) {                      // RGBA8u::Unpack, Texture.h:28-36
+    const float scale = 1.0f / 255;
+    out[0] = (float)(p & 255) * scale; out[1] = (float)((p >> 8) & 255) * scale; out[2] = (float)((p >> 16) & 255) * scale;
+}
+
+// enum class DebugLayer (Shading.h:8)
+enum { kLayerNone = 0, kLayerBaseColor, kLayerNormals, kLayerMetallicRoughness, kLayerMeshletId, kLayerTriangleId,
+       kLayerOverdrawPixel, kLayerOverdrawQuad };
+
 }  // namespace
+
+static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                              const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                              const swr_light* lights, uint32_t numLights,
+                              const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer);
 
 extern "C" {
 
@@ -220,6 +247,27 @@ void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint3
                       const swr_light* lights, uint32_t numLights,
                       const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
                       const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd) {
+    resolve_rows_impl(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
+                      objectToWorld3, invScreenProj, viewPos, exposure, yBegin, yEnd, kLayerNone);
+}
+
+// ShadingContext::ResolveDebug (Shading.cpp:734-773): layer 0 is overwritten with the visualisation of `layer`
+// (DebugLayer, Shading.h:8); sky pixels (depth <= 0) get a 4x4 checkerboard of 0xFFA0A0A0 / 0xFFFFFFFF.
+void orc_resolve_debug(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                       const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                       const float* objectToClip, const float* objectToWorld3, const float* invScreenProj, int layer) {
+    const float zero[3] = { 0, 0, 0 };
+    resolve_rows_impl(color, depth, width, height, meshlets, materials, textures, nullptr, 0, objectToClip,
+                      objectToWorld3, invScreenProj, zero, 1.0f, 0, height, layer);
+}
+
+}  // extern "C"
+
+static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                              const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                              const swr_light* lights, uint32_t numLights,
+                              const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer) {
     const float scaleU = 2.0f / (float)width, scaleV = 2.0f / (float)height;       // Rasterizer.h:226
     const float centerU = 0.5f * scaleU - 1.0f, centerV = 0.5f * scaleV - 1.0f;    // :227
     const V3 view = { viewPos[0], viewPos[1], viewPos[2] };
@@ -248,7 +296,16 @@ void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint3
             float outColor[N][3];
             for (int i = 0; i < N; i++) outColor[i][0] = outColor[i][1] = outColor[i][2] = 0.0f;
 
-            if (anySurface) {
+            if (debugLayer >= kLayerMeshletId) {                                    // Shading.cpp:755-766: straight from the colour word
+                for (int i = 0; i < N; i++) {
+                    uint32_t d = tileData[i];
+                    float* o = outColor[i];
+                    if (debugLayer == kLayerMeshletId) unpack_rgba8((d / SWR_MAX_PRIMS) * 123456789u, o);
+                    else if (debugLayer == kLayerTriangleId) unpack_rgba8(d * 123456789u, o);
+                    else if (debugLayer == kLayerOverdrawPixel) colormap_turbo((float)(d >> 16) / 30.0f, o);
+                    else colormap_turbo(((float)(d >> 16) + (float)(d & 0xFFFF) * 0.5f) / 30.0f, o);
+                }
+            } else if (anySurface) {
                 // ---- ResolveSurface (Shading.cpp:472-579)
                 float bary[N][3], ddx[N][3], ddy[N][3];
                 uint32_t packedTC[N][3], packedNT[N][3], handed[N], materialId[N];
@@ -360,6 +417,15 @@ void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint3
                                 (float)((packedNMR[i] >> 24) & 255) * (1.0f / 255) };
                 }
 
+                if (debugLayer != kLayerNone) {                                     // Shading.cpp:749-754
+                    for (int i = 0; i < N; i++) {
+                        if (sky[i]) continue;
+                        float* o = outColor[i];
+                        if (debugLayer == kLayerBaseColor) unpack_rgba8(surf[i].albedo, o);
+                        else if (debugLayer == kLayerNormals) { o[0] = surf[i].normal.x * 0.5f + 0.5f; o[1] = surf[i].normal.y * 0.5f + 0.5f; o[2] = surf[i].normal.z * 0.5f + 0.5f; }
+                        else { o[0] = surf[i].metallic; o[1] = surf[i].roughness; o[2] = 0.0f; }
+                    }
+                } else {
                 // ---- EvalLighting (Shading.cpp:602-645), tile-wide like the reference: the two
                 // `simd::all(...) continue` early-outs (:620, :623) span the non-sky lanes (pinned, see header).
                 const float reflectance = 0.5f;
@@ -418,6 +484,13 @@ void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint3
                     if (sky[i]) continue;
                     for (int k = 0; k < 3; k++) outColor[i][k] = c[i][k] + base[i][k] * 0.05f;   // :642
                 }
+                }
+            }
+            if (debugLayer != kLayerNone) {                                          // Shading.cpp:768-771
+                const uint32_t background = ((x0 ^ y0) & 4) ? 0xFFA0A0A0u : 0xFFFFFFFFu;
+                for (int i = 0; i < N; i++)
+                    tileData[i] = sky[i] ? background : pack_rgba8(outColor[i][0], outColor[i][1], outColor[i][2], 1.0f);
+                continue;
             }
             // tonemap + pack (:680-688, Tonemap_Unreal :221-226)
             for (int i = 0; i < N; i++) {
@@ -431,6 +504,8 @@ void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t width, uint3
         }
     }
 }
+
+extern "C" {
 
 void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
                  const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,

@@ -62,8 +62,9 @@ class Framebuffer:
 
 def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, count: int, object_to_clip,
                   cull_bitmap=None, materials=None, guardband: bool = True, counters=None, textures=None,
-                  binned: bool = True, clipping: bool = False) -> np.ndarray:
-    """Rasterizer::DrawMeshlets + VisBufferShader on the CPU. Returns the 4 integer perf counters.
+                  binned: bool = True, clipping: bool = False, overdraw: bool = False) -> np.ndarray:
+    """Rasterizer::DrawMeshlets + VisBufferShader (or, with `overdraw`, OverdrawShader = FS_Overdraw, Shading.cpp:333-342,
+    :656) on the CPU. Returns the 4 integer perf counters.
 
     With `textures`, alpha-tested materials (AlphaCutoff < 255) run FS_EncodeSurfaceId<true>; without, every
     triangle takes the opaque program. binned=False selects DrawMeshletsST's treatment of non-trivial triangles:
@@ -77,7 +78,8 @@ def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, co
     descs, keep = (None, None) if not textures else _texture_descs(textures)
     lib().orc_draw_meshlets_ex(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
                                C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats, descs,
-                               C.c_uint32((1 if guardband else 0) | (0 if binned else (2 if clipping else 4))), _p(counters))
+                               C.c_uint32((1 if guardband else 0) | (0 if binned else (2 if clipping else 4)) | (8 if overdraw else 0)),
+                               _p(counters))
     return counters
 
 
@@ -117,6 +119,21 @@ def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, 
                       C.c_float(exposure))
     if world_to_clip is not None and len(lights):
         draw_light_markers(fb, lights, world_to_clip)
+
+
+DEBUG_LAYERS = ["None", "BaseColor", "Normals", "MetallicRoughness", "MeshletId", "TriangleId", "OverdrawPixel", "OverdrawQuad"]
+
+
+def resolve_debug(fb: Framebuffer, meshlets: np.ndarray, materials, textures, layer, object_to_clip, object_to_world3,
+                  inv_screen_proj, **_unused):
+    """ShadingContext::ResolveDebug (Shading.cpp:734-773) on the CPU; `layer` is a DebugLayer name or value (Shading.h:8)."""
+    layer = DEBUG_LAYERS.index(layer) if isinstance(layer, str) else int(layer)
+    assert 1 <= layer <= 7
+    descs, keep = _texture_descs(textures)
+    o2w = np.ascontiguousarray(np.asarray(object_to_world3, dtype=np.float32).reshape(9))
+    lib().orc_resolve_debug(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
+                            _p(materials) if len(materials) else None, descs, _p(_mat(object_to_clip)), _p(o2w),
+                            _p(_mat(inv_screen_proj)), C.c_int(layer))
 
 
 def draw_light_markers(fb: Framebuffer, lights, world_to_clip) -> None:
