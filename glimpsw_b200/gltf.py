@@ -1,0 +1,259 @@
+"""Host-side scene import: glTF 2.0 -> the path's input structures.
+
+Mirrors `Scene::ImportGltf` (src/SwRast/Scene.cpp:156-368) and its helpers `LoadTextures` / `CombineNormalMR` /
+`InsertEmissiveMask` (:17-102): one material + one layered RGBA8 texture per glTF material, every mesh primitive split
+into `Meshlet`s (<= 64 vertices, <= 128 triangles, SoA positions, fp16 UVs, octahedron-packed normal + tangent,
+handedness bits), nodes walked depth-first with `GlobalTransform = parent * local`, KHR_lights_punctual lights.
+
+What differs from the reference, by necessity (none of its third-party importers exist in this image):
+  * cgltf -> the JSON + buffer parsing below (`.gltf` with external / data-URI buffers, and `.glb`);
+  * meshoptimizer's `meshopt_buildMeshlets` -> the greedy scan of `scenes.meshletize` (different meshlet boundaries
+    = different surface ids, same geometry) and a centroid bounding sphere instead of `meshopt_computeMeshletBounds`;
+  * stb_image -> Pillow for the texture files.
+Everything downstream (the meshlet bytes, materials, texture layout, uniforms) is the reference's format, so an imported
+scene goes through `api.Rasterizer.upload_scene` / the oracle like the procedural ones.
+"""
+from __future__ import annotations
+
+import base64
+import json
+import math
+import os
+import struct
+
+import numpy as np
+
+from . import camera as cam
+from . import textures as tx
+from .layout import LIGHT_DTYPE, MATERIAL_DTYPE
+from .scenes import DrawNode, SceneData, concat_meshlets, meshletize
+
+f32 = np.float32
+NO_MATERIAL = 0xFFFFFFFF
+
+_COMPONENT = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+_WIDTH = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
+
+
+class GltfFile:
+    """The parsed JSON plus its binary buffers (cgltf_parse_file + cgltf_load_buffers, Scene.cpp:157-168)."""
+
+    def __init__(self, path: str):
+        self.base = os.path.dirname(os.path.abspath(path))
+        raw = open(path, "rb").read()
+        glb_bin = None
+        if raw[:4] == b"glTF":                                        # binary container: JSON chunk + optional BIN chunk
+            _, _, total = struct.unpack_from("<III", raw, 0)
+            off, chunks = 12, []
+            while off < total:
+                n, kind = struct.unpack_from("<II", raw, off)
+                chunks.append((kind, raw[off + 8: off + 8 + n]))
+                off += 8 + n
+            self.json = json.loads(next(c for k, c in chunks if k == 0x4E4F534A))
+            glb_bin = next((c for k, c in chunks if k == 0x004E4942), None)
+        else:
+            self.json = json.loads(raw)
+        self.buffers = []
+        for b in self.json.get("buffers", []):
+            uri = b.get("uri")
+            if uri is None:
+                data = glb_bin
+            elif uri.startswith("data:"):
+                data = base64.b64decode(uri.split(",", 1)[1])
+            else:
+                data = open(os.path.join(self.base, uri), "rb").read()
+            if data is None or len(data) < b["byteLength"]:
+                raise RuntimeError("Failed to load associated GLTF data")     # Scene.cpp:166
+            self.buffers.append(np.frombuffer(data, dtype=np.uint8))
+
+    def accessor(self, index: int) -> np.ndarray:
+        """cgltf_accessor_unpack_*: [count, width] array in the accessor's component type (normalized ints -> float)."""
+        a = self.json["accessors"][index]
+        dt, width, count = _COMPONENT[a["componentType"]], _WIDTH[a["type"]], a["count"]
+        if "bufferView" not in a:
+            out = np.zeros((count, width), dtype=dt)
+        else:
+            v = self.json["bufferViews"][a["bufferView"]]
+            start = v.get("byteOffset", 0) + a.get("byteOffset", 0)
+            item = np.dtype(dt).itemsize * width
+            stride = v.get("byteStride", 0) or item
+            buf = self.buffers[v["buffer"]]
+            idx = start + np.arange(count)[:, None] * stride + np.arange(item)[None, :]
+            out = buf[idx].copy().view(dt).reshape(count, width)
+        if a.get("normalized") and dt != np.float32:
+            out = np.maximum(out.astype(f32) / float(np.iinfo(dt).max), -1.0)
+        return out
+
+    def image_rgba(self, texture_info) -> np.ndarray | None:
+        """LoadImage (Scene.cpp:51-76): the RGBA8 pixels of a texture view, or None when the view is empty."""
+        if not texture_info:
+            return None
+        tex = self.json["textures"][texture_info["index"]]
+        if "source" not in tex:
+            return None
+        img = self.json["images"][tex["source"]]
+        from PIL import Image
+        import io
+        if "uri" in img and not img["uri"].startswith("data:"):
+            src = os.path.join(self.base, img["uri"])
+        elif "uri" in img:
+            src = io.BytesIO(base64.b64decode(img["uri"].split(",", 1)[1]))
+        else:
+            v = self.json["bufferViews"][img["bufferView"]]
+            o = v.get("byteOffset", 0)
+            src = io.BytesIO(self.buffers[v["buffer"]][o: o + v["byteLength"]].tobytes())
+        try:
+            return np.asarray(Image.open(src).convert("RGBA"), dtype=np.uint8)
+        except Exception as exc:
+            raise RuntimeError("Failed to load image") from exc                # Scene.cpp:68
+
+
+def _words(rgba: np.ndarray) -> np.ndarray:
+    return rgba.astype(np.uint32) @ np.array([1, 1 << 8, 1 << 16, 1 << 24], dtype=np.uint32)
+
+
+def combine_normal_mr(normal: np.ndarray, mr: np.ndarray | None) -> np.ndarray:
+    """CombineNormalMR (Scene.cpp:17-36): renormalized normal.xy in RG, metallic in B, roughness in A."""
+    out = normal.copy()
+    n = normal[..., :3].astype(f32) / f32(127.0) - f32(1.0)
+    n = n / np.sqrt((n * n).sum(axis=-1, keepdims=True), dtype=f32) * f32(127.0) + f32(127.0)
+    r = np.floor(np.abs(n) + f32(0.5)) * np.sign(n)                            # roundf: half away from zero
+    out[..., 0] = r[..., 0].astype(np.uint8)
+    out[..., 1] = r[..., 1].astype(np.uint8)
+    if mr is not None:
+        out[..., 2] = mr[..., 2]
+        out[..., 3] = mr[..., 1]
+    return out
+
+
+def insert_emissive_mask(base: np.ndarray, emissive: np.ndarray) -> np.ndarray:
+    """InsertEmissiveMask (Scene.cpp:38-49): alpha 255 marks emissive texels, everything else is capped at 254."""
+    out = base.copy()
+    lit = (emissive[..., :3] > 8).any(axis=-1)
+    out[..., 3] = np.where(lit, 255, np.minimum(base[..., 3], 254)).astype(np.uint8)
+    return out
+
+
+def load_textures(g: GltfFile, mat: dict) -> tx.TextureData:
+    """LoadTextures (Scene.cpp:78-102)."""
+    pbr = mat.get("pbrMetallicRoughness", {})
+    base = g.image_rgba(pbr.get("baseColorTexture"))
+    if base is None:
+        return tx.create_texture(4, 4, 1, 1)
+    h, w = base.shape[:2]
+    normal, mr, emissive = g.image_rgba(mat.get("normalTexture")), g.image_rgba(pbr.get("metallicRoughnessTexture")), g.image_rgba(mat.get("emissiveTexture"))
+    has_normals = normal is not None and normal.shape[:2] == (h, w)
+    has_emissive = emissive is not None and emissive.shape[:2] == (h, w)
+    tex = tx.create_texture(w, h, 8, 3 if has_emissive else (2 if has_normals else 1))
+    if has_normals:
+        tx.set_pixels(tex, _words(combine_normal_mr(normal, mr if mr is not None and mr.shape[:2] == (h, w) else None)), layer=1)
+    if has_emissive:
+        base = insert_emissive_mask(base, emissive)
+        tx.set_pixels(tex, _words(emissive), layer=2)
+    tx.set_pixels(tex, _words(base), layer=0)
+    tx.generate_mips(tex)
+    return tex
+
+
+def _node_local(n: dict) -> np.ndarray:
+    """cgltf_node_transform_local: the node's matrix, or T * R * S — here as a mathematical (row, column) float64 matrix;
+    import_gltf transposes to the package's column-major [c, r] float32 convention when it stores a node."""
+    if "matrix" in n:
+        return np.asarray(n["matrix"], dtype=np.float64).reshape(4, 4).T        # glTF stores column-major
+    t = np.eye(4)
+    t[:3, 3] = n.get("translation", (0, 0, 0))
+    x, y, z, w = n.get("rotation", (0, 0, 0, 1))
+    r = np.eye(4)
+    r[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                 [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                 [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+    s = np.diag(list(n.get("scale", (1, 1, 1))) + [1.0])
+    return t @ r @ s
+
+
+def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Camera | None = None,
+                flip_winding: bool = False) -> SceneData:
+    """Scene::ImportGltf. Returns a SceneData (meshlets, one DrawNode per glTF node with a mesh, materials, textures,
+    lights). `flip_winding` swaps two indices of every triangle (for assets authored with the other front face)."""
+    g = GltfFile(path)
+    js = g.json
+    materials = np.zeros(len(js.get("materials", [])), dtype=MATERIAL_DTYPE)
+    textures = []
+    for i, mat in enumerate(js.get("materials", [])):                          # Scene.cpp:174-184
+        textures.append(load_textures(g, mat))
+        materials[i]["TextureId"] = i
+        materials[i]["IsDoubleSided"] = 1 if mat.get("doubleSided") else 0
+        cutoff = mat.get("alphaCutoff", 0.5)
+        materials[i]["AlphaCutoff"] = int(cutoff * 255.0 + 0.5) & 255 if mat.get("alphaMode") == "MASK" else 255
+
+    parts, ranges, cursor = [], [], 0
+    for mesh in js.get("meshes", []):                                          # Scene.cpp:193-283
+        start = cursor
+        for prim in mesh["primitives"]:
+            if prim.get("mode", 4) != 4:
+                continue
+            attrs = prim["attributes"]
+            pos = g.accessor(attrs["POSITION"]).astype(f32)
+            idx = g.accessor(prim["indices"]).reshape(-1).astype(np.int64) if "indices" in prim else np.arange(len(pos), dtype=np.int64)
+            tris = idx[: len(idx) // 3 * 3].reshape(-1, 3)
+            if flip_winding:
+                tris = tris[:, [0, 2, 1]]
+            uv = g.accessor(attrs["TEXCOORD_0"]).astype(f32) if "TEXCOORD_0" in attrs else None
+            nrm = g.accessor(attrs["NORMAL"]).astype(f32) if "NORMAL" in attrs else None
+            tan = g.accessor(attrs["TANGENT"]).astype(f32) if "TANGENT" in attrs and nrm is not None else None
+            if nrm is not None and tan is None:
+                tan = np.zeros((len(pos), 4), dtype=f32)                        # glm::vec4 tangent = 0 (Scene.cpp:258)
+            mat_id = prim.get("material", None)
+            m = meshletize(pos, tris, uv=uv, normals=nrm, tangents=tan,
+                           material_id=NO_MATERIAL if mat_id is None else mat_id,
+                           alpha_cutoff=255 if mat_id is None else int(materials[mat_id]["AlphaCutoff"]))
+            parts.append(m)
+            cursor += len(m)
+        ranges.append((start, cursor))
+    meshlets = concat_meshlets(parts) if parts else meshletize(np.zeros((0, 3), dtype=f32), np.zeros((0, 3), dtype=np.int64))
+
+    nodes, lights = [], []
+    punctual = js.get("extensions", {}).get("KHR_lights_punctual", {}).get("lights", [])
+
+    def recurse(index: int, parent: np.ndarray):                               # Scene.cpp:286-352 (pre-order DFS)
+        n = js["nodes"][index]
+        glob = parent @ _node_local(n)
+        if "mesh" in n:
+            a, b = ranges[n["mesh"]]
+            if b > a:
+                nodes.append(DrawNode(a, b - a, np.ascontiguousarray(glob.T.astype(f32))))
+        li = n.get("extensions", {}).get("KHR_lights_punctual", {}).get("light")
+        if li is not None:
+            src = punctual[li]
+            l = np.zeros(1, dtype=LIGHT_DTYPE)
+            l["Type"] = {"directional": 0, "point": 1, "spot": 2}[src["type"]]
+            l["Position"] = glob[:3, 3]
+            d = -glob[:3, 2]
+            l["Direction"] = d / np.linalg.norm(d)
+            l["Color"] = src.get("color", (1, 1, 1))
+            l["Intensity"] = src.get("intensity", 1.0)
+            rng = float(src.get("range", 0.0))
+            rng = rng if rng > 0 else 1e6                                       # Light::SetRadius (Scene.h:65-68)
+            l["Radius"] = rng
+            l["InvRadiusSq"] = f32(1.0) / (f32(rng) * f32(rng))
+            spot = src.get("spot", {})
+            inner, outer = float(spot.get("innerConeAngle", 0.0)), float(spot.get("outerConeAngle", math.pi / 4))
+            l["SpotInnerAngle"], l["SpotOuterAngle"] = inner, outer             # Light::SetSpotAngles (Scene.h:69-74)
+            scale = f32(1.0) / max(f32(math.cos(inner)) - f32(math.cos(outer)), f32(1e-4))
+            l["SpotScale"], l["SpotOffset"] = scale, -f32(math.cos(outer)) * scale
+            lights.append(l)
+        for c in n.get("children", []):
+            recurse(c, glob)
+
+    scene_def = js["scenes"][js.get("scene", 0)] if js.get("scenes") else {"nodes": list(range(len(js.get("nodes", []))))}
+    for root in scene_def.get("nodes", []):
+        recurse(root, np.eye(4))
+
+    if camera is None:                                                         # the pose RasterBench.cpp:68 hard-codes
+        camera = cam.Camera(position=(-0.46608772755098471, 8.4925445559659511, -1.7022251220187172),
+                            euler=(-3.13643026, -1.4724431), fov_deg=90.0, aspect=width / height)
+    scene = SceneData(os.path.splitext(os.path.basename(path))[0], meshlets, nodes, camera, width, height)
+    scene.materials = materials
+    scene.textures = textures
+    scene.lights = np.concatenate(lights) if lights else np.zeros(0, dtype=LIGHT_DTYPE)
+    return scene

@@ -114,35 +114,37 @@ public:
         return visible;
     }
 
-    // Rasterizer::DrawMeshlets(fb, count, {ShadingContext::VisBufferShader, &ctx}) — Rasterizer.cpp:493
+    // Rasterizer::DrawMeshlets(fb, count, {table, &ctx}) — Rasterizer.cpp:493. `table` names the reference's shader table:
+    // SWRB_PROGRAM_VISBUFFER = ShadingContext::VisBufferShader, SWRB_PROGRAM_OVERDRAW = ShadingContext::OverdrawShader
+    // (the choice the Playground makes per frame, Main.cpp:204-209).
     template <class Ctx>
-    void DrawMeshlets(Framebuffer& fb, uint32_t count, const Ctx& ctx) {
+    void DrawMeshlets(Framebuffer& fb, uint32_t count, const Ctx& ctx, swrb_program table = SWRB_PROGRAM_VISBUFFER) {
         apply_flags();
         swrb_draw_desc d{};
         d.MeshletOffset = ctx.MeshletOffset;
         d.MeshletCount = count;
         std::memcpy(d.ObjectToClip, &ctx.ObjectToClipMat[0][0], sizeof d.ObjectToClip);
         d.CullBitmapHost = reinterpret_cast<const uint16_t*>(ctx.MeshletCullBitmap);
-        check(swrb_draw_meshlets(fb.handle(), _scene, &d));
+        check(swrb_draw_batch_program(fb.handle(), _scene, &d, 1, table));
     }
     // The per-node loop of Main.cpp:216-240 as one submission.
-    void DrawBatch(Framebuffer& fb, const std::vector<swrb_draw_desc>& draws) {
+    void DrawBatch(Framebuffer& fb, const std::vector<swrb_draw_desc>& draws, swrb_program table = SWRB_PROGRAM_VISBUFFER) {
         apply_flags();
-        check(swrb_draw_batch(fb.handle(), _scene, draws.data(), (uint32_t)draws.size()));
+        check(swrb_draw_batch_program(fb.handle(), _scene, draws.data(), (uint32_t)draws.size(), table));
     }
 
     // ShadingContext::Resolve(rast, fb) — Shading.cpp:658. invScreenProj = GetInverseScreenProjMatrix(ctx.WorldToClipMat,
     // {fb.Width, fb.Height}) (Camera.h:140-146), computed by the caller exactly as today.
     template <class Ctx, class Mat4>
     void Resolve(Framebuffer& fb, const Ctx& ctx, const Mat4& invScreenProj) {
-        swrb_shading_uniforms u{};
-        std::memcpy(u.WorldToClip, &ctx.WorldToClipMat[0][0], sizeof u.WorldToClip);
-        std::memcpy(u.ObjectToClip, &ctx.ObjectToClipMat[0][0], sizeof u.ObjectToClip);
-        std::memcpy(u.ObjectToWorld, &ctx.ObjectToWorldMat[0][0], sizeof u.ObjectToWorld);
-        std::memcpy(u.InvScreenProj, &invScreenProj[0][0], sizeof u.InvScreenProj);
-        std::memcpy(u.ViewPos, &ctx.ViewPos[0], sizeof u.ViewPos);
-        u.Exposure = ctx.Exposure;
+        const swrb_shading_uniforms u = uniforms(ctx, invScreenProj);
         check(swrb_resolve(fb.handle(), _scene, &u));
+    }
+    // ShadingContext::ResolveDebug(rast, fb, layer) — Shading.cpp:734; layer = enum class DebugLayer (Shading.h:8)
+    template <class Ctx, class Mat4>
+    void ResolveDebug(Framebuffer& fb, const Ctx& ctx, const Mat4& invScreenProj, swrb_debug_layer layer) {
+        const swrb_shading_uniforms u = uniforms(ctx, invScreenProj);
+        check(swrb_resolve_debug(fb.handle(), _scene, &u, layer));
     }
 
     // perf::GetCurrent(PerfCounter::…) — Rasterizer.h:381-395
@@ -158,6 +160,17 @@ public:
     swrb_scene* scene() const { return _scene; }
 
 private:
+    template <class Ctx, class Mat4>
+    static swrb_shading_uniforms uniforms(const Ctx& ctx, const Mat4& invScreenProj) {
+        swrb_shading_uniforms u{};
+        std::memcpy(u.WorldToClip, &ctx.WorldToClipMat[0][0], sizeof u.WorldToClip);
+        std::memcpy(u.ObjectToClip, &ctx.ObjectToClipMat[0][0], sizeof u.ObjectToClip);
+        std::memcpy(u.ObjectToWorld, &ctx.ObjectToWorldMat[0][0], sizeof u.ObjectToWorld);
+        std::memcpy(u.InvScreenProj, &invScreenProj[0][0], sizeof u.InvScreenProj);
+        std::memcpy(u.ViewPos, &ctx.ViewPos[0], sizeof u.ViewPos);
+        u.Exposure = ctx.Exposure;
+        return u;
+    }
     void apply_flags() {
         check(swrb_device_set_flags(_dev, (EnableBinning ? SWRB_FLAG_BINNING : 0u) | (EnableClipping ? SWRB_FLAG_CLIPPING : 0u) |
                                               (EnableGuardband ? SWRB_FLAG_GUARDBAND : 0u)));

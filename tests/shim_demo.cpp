@@ -52,8 +52,20 @@ int main() {
         fb.GetPixels(0, ids.data(), W);
         uint32_t covered = 0;
         for (uint32_t v : ids) covered += v != 0xFFFFFFFFu;
-        std::printf("OK %u %u %llu %u\n", covered, ids[(H / 2 - 4) * W + (W / 2 - 4)],
-                    (unsigned long long)rast.GetCounter(SWR_PERF_TrianglesRasterized), visible);
+        const unsigned long long rasterized = rast.GetCounter(SWR_PERF_TrianglesRasterized);
+
+        // the Playground's overdraw view (Main.cpp:204-209, :251): OverdrawShader, then ResolveDebug(OverdrawPixel)
+        swrb200::Framebuffer od = rast.CreateFramebuffer(W, H);
+        od.Clear(0u, 0.0f);
+        rast.DrawMeshlets(od, 1, ctx, SWRB_PROGRAM_OVERDRAW);
+        rast.DrawMeshlets(od, 1, ctx, SWRB_PROGRAM_OVERDRAW);
+        std::vector<uint32_t> counts(W * H);
+        od.GetPixels(0, counts.data(), W);
+        uint32_t twice = 0;
+        for (uint32_t v : counts) twice += (v >> 16) == 2u;
+        rast.ResolveDebug(od, ctx, I, SWRB_LAYER_OVERDRAW_PIXEL);
+        od.GetPixels(0, counts.data(), W);
+        std::printf("OK %u %u %llu %u %u %08x\n", covered, ids[(H / 2 - 4) * W + (W / 2 - 4)], rasterized, visible, twice, counts[0]);
     } catch (const std::exception& e) {
         std::printf("NO_DEVICE %s\n", e.what());
     }

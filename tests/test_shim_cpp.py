@@ -40,3 +40,5 @@ def test_shim_renders_like_the_oracle(tmp_path, orc):
     ids = fb.get_pixels(0)
     assert int(c[1]) == 1 and int((ids != 0xFFFFFFFF).sum()) > 0
     assert [int(out[1]), int(out[2]), int(out[3]), int(out[4])] == [int((ids != 0xFFFFFFFF).sum()), int(ids[28, 28]), 1, 1]
+    # OverdrawShader drawn twice counts every covered pixel twice; ResolveDebug paints sky fragment (0,0) white
+    assert int(out[5]) == int((ids != 0xFFFFFFFF).sum()) and out[6] == "ffffffff"
