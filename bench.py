@@ -327,7 +327,7 @@ def run_ours(args):
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes": stages[dom]["algorithmic_bytes"],
                 "avg_launch_us": stages[dom]["us"],
                 "note": "kernel time from CUDA events on the launching stream in latency mode (L2 evicted before each frame); the "
-                        "kernel is instruction-issue bound, not HBM bound (profiles/r01_summary.md)"}
+                        "kernel is instruction-issue / load-latency bound, not HBM bound: ~580 warp instructions per pixel for 12 algorithmic bytes (profiles/r01_summary.md)"}
     roofline["traffic"] = traffic.get(roofline["kernel"])
     if roofline["traffic"] is not None:
         roofline["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"

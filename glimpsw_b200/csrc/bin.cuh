@@ -71,7 +71,8 @@ k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, const uint32_t
     __shared__ uint32_t warpSums[32];
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t n = ctl->overflow ? 0u : ctl->triCount;
-    if (n == 0 && blockIdx.x != 0) return;
+    if (n == 0) return;     // no records (every triangle was rasterized inline): k_frame_begin left binTotal / numActiveTiles at 0,
+                            // which is all the tile rasterizer looks at before it returns
 
     // ---- pass 2: counts (L2, produced by the mesh kernel's atomics) -> exclusive offsets in shared memory
     for (uint32_t i = threadIdx.x; i < numTiles; i += kScatterThreads) sOffset[i] = __ldcg(tileCount + i);
