@@ -196,22 +196,11 @@ def run_ours(args):
             with torch.cuda.stream(comm):                       # beside the next frames' kernels
                 comm.wait_event(c.resolved)
                 if peers is not None:
-                    dbg = os.environ.get("SWRB_BENCH_P2P_DEBUG", "")       # diagnostic switches: "nosignal", "nocopy"
-                    if "nosignal" not in dbg:
-                        peers.before_write(slot, comm)
-                    if "nocopy" in dbg:
-                        pass
-                    elif "ce" in dbg:      # de-tile locally, then a copy-engine transfer into rank 0's memory
-                        c.fb.get_pixels_device(0, composites[slot].data_ptr(), cuda_stream=comm.cuda_stream)
-                        peers.root[slot, rank].copy_(composites[slot], non_blocking=True)
-                    else:
-                        c.fb.get_pixels_device(0, peers.dst_ptr(slot), cuda_stream=comm.cuda_stream)   # GetPixels straight into rank 0's memory
+                    peers.send(c.fb, slot, comm)                # GetPixels straight into rank 0's memory (+ slot flow control)
                     if c.copied is None:
                         c.copied = torch.cuda.Event()           # per context: a shared per-slot event would be re-recorded by
                     c.copied.record(comm)                       # later frames and chain consecutive frames together
-                    if "nosignal" not in dbg:
-                        peers.after_write(slot, comm)
-                        peers.collect(slot, coll)               # rank 0 waits for its peers on a third stream
+                    peers.collect(c.rast, slot, coll)           # rank 0 waits for its peers on a third stream
                     gather_done[slot].record(coll if rank == 0 else comm)
                 else:
                     comm.wait_event(gather_done[slot])

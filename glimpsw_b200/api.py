@@ -51,6 +51,7 @@ EXPORTS = [
     "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
     "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
     "swrb_hiz_download", "swrb_cull_meshlets_hiz", "swrb_draw_batch_program", "swrb_resolve_debug",
+    "swrb_fb_send_pixels", "swrb_peer_collect",
 ]
 
 PROGRAM_VISBUFFER, PROGRAM_OVERDRAW = 0, 1     # ShadingContext::VisBufferShader / OverdrawShader (Shading.h:49)
@@ -76,6 +77,10 @@ class TextureDesc(C.Structure):
     _fields_ = [("Width", C.c_uint32), ("Height", C.c_uint32), ("MipLevels", C.c_uint32), ("NumLayers", C.c_uint32),
                 ("RowShift", C.c_uint32), ("LayerStride", C.c_uint32), ("MipOffsets", C.c_uint32 * 16),
                 ("Data", C.c_void_p)]
+
+
+class PeerSync(C.Structure):     # swrb_peer_sync
+    _fields_ = [("WaitFlag", C.c_void_p), ("WaitValue", C.c_uint64), ("SignalFlag", C.c_void_p), ("SignalValue", C.c_uint64)]
 
 
 class FbInfo(C.Structure):
@@ -169,6 +174,13 @@ class Framebuffer:
         else:
             _check(self.rast.lib.swrb_fb_get_pixels_device_on_stream(self._h, C.c_uint32(layer), C.c_void_p(device_ptr),
                                                                      C.c_uint32(stride or self.width), C.c_void_p(cuda_stream)))
+
+    def send_pixels(self, layer: int, device_ptr: int, cuda_stream: int, wait_flag: int = 0, wait_value: int = 0,
+                    signal_flag: int = 0, signal_value: int = 0, stride: int | None = None):
+        """GetPixels into another GPU's memory with the slot flow control folded into the kernel (swrb_fb_send_pixels)."""
+        ps = PeerSync(wait_flag or None, wait_value, signal_flag or None, signal_value)
+        _check(self.rast.lib.swrb_fb_send_pixels(self._h, C.c_uint32(layer), C.c_void_p(device_ptr), C.c_uint32(stride or self.width),
+                                                 C.c_void_p(cuda_stream), C.byref(ps)))
 
     def destroy(self):
         if self._h:
@@ -402,6 +414,12 @@ class Rasterizer:
 
     def resolve_prebuilt(self, fb: Framebuffer, scene: Scene, uniforms: ShadingUniforms):
         _check(self.lib.swrb_resolve(fb._h, scene._h, C.byref(uniforms)))
+
+    def peer_collect(self, cuda_stream: int, ready_flags_ptr: int, n: int, expected: int, ack_flag_ptrs, ack_value: int):
+        """Consumer side of the composite exchange (swrb_peer_collect): wait for n ready flags, then ack every producer."""
+        arr = (C.c_void_p * n)(*[int(p) for p in ack_flag_ptrs])
+        _check(self.lib.swrb_peer_collect(self._h, C.c_void_p(cuda_stream), C.c_void_p(ready_flags_ptr), C.c_uint32(n),
+                                          C.c_uint64(expected), arr, C.c_uint64(ack_value)))
 
     def sync(self):
         _check(self.lib.swrb_sync(self._h))

@@ -101,4 +101,79 @@ k_fb_detile(const uint4* __restrict__ layer, uint32_t* __restrict__ dst, uint32_
     }
 }
 
+// ---- multi-GPU composite exchange over NVLink peer memory ------------------------------------------------
+// The de-tile kernel IS the transfer: it stores the finished view straight into the consumer GPU's memory, and the
+// flow control that a collective library would add as extra kernels is folded into it:
+//   * before the first store every block waits (one spinning thread) until the consumer has released the slot
+//     (`waitFlag`, in this GPU's memory, written by the consumer's k_peer_collect);
+//   * after the last store of the last block the producer raises the slot's ready flag in the CONSUMER's memory
+//     (system-scope fence before it, so the pixels are visible there first).
+// Flags carry monotonically increasing use counts, so nothing is ever reset across the link.
+struct PeerSync {
+    const unsigned long long* waitFlag;   // null: nothing to wait for
+    unsigned long long waitValue;
+    unsigned long long* signalFlag;       // null: no signal
+    unsigned long long signalValue;
+    uint32_t* blockCounter;               // this device's scratch counter, zero between launches
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_fb_detile_send(const uint4* __restrict__ layer, uint32_t* __restrict__ dst, uint32_t width, uint32_t height, uint32_t stride, PeerSync ps) {
+    if (ps.waitFlag != nullptr) {
+        if (threadIdx.x == 0) while (ld_acquire_sys(ps.waitFlag) < ps.waitValue) __nanosleep(100);
+        __syncthreads();
+    }
+    const uint32_t numVec = width * height / 4, tilesPerRow = width >> 2;
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < numVec; i0 += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t i = i0 + k * step;
+            if (i < numVec) v[k] = layer[i];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t i = i0 + k * step;
+            if (i < numVec) {
+                uint32_t row = i & 3u, tile = i >> 2;
+                uint32_t tx = tile % tilesPerRow, ty = tile / tilesPerRow;
+                *reinterpret_cast<uint4*>(dst + (size_t)(ty * 4 + row) * stride + tx * 4) = v[k];
+            }
+        }
+    }
+    if (ps.signalFlag != nullptr) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t done = atomicAdd(ps.blockCounter, 1u) + 1u;
+            if (done == gridDim.x) {
+                *ps.blockCounter = 0;
+                __threadfence_system();
+                st_release_sys(ps.signalFlag, ps.signalValue);
+            }
+        }
+    }
+}
+
+// Consumer side, one launch per slot: wait until every producer has raised its ready flag for this use of the slot
+// (flags are in this GPU's memory), then release the slot on every producer (their ack flags, over NVLink).
+struct PeerAcks { unsigned long long* flag[15]; };
+__global__ void __launch_bounds__(32)
+k_peer_collect(const unsigned long long* __restrict__ readyFlags, uint32_t n, unsigned long long expected, PeerAcks acks, unsigned long long ackValue) {
+    const uint32_t t = threadIdx.x;
+    if (t < n) while (ld_acquire_sys(readyFlags + t) < expected) __nanosleep(100);
+    __syncwarp();
+    if (t < n) st_release_sys(acks.flag[t], ackValue);
+}
+
 }  // namespace swrb

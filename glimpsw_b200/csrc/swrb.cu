@@ -118,6 +118,7 @@ struct swrb_device {
     // Per-vertex {x/w, y/w, 1/w, z/w} of the last batch, written by the mesh kernel for the resolve pass.
     // swrb_resolve may read it only if every surface id in the framebuffer provably comes from that batch
     // and the batch used the one matrix the resolve is handed (see clip_cache_usable).
+    uint32_t* peerCounter = nullptr;      // block counter of k_fb_detile_send (multi-GPU composite exchange)
     float4* clipCache = nullptr;
     uint64_t clipCacheCap = 0;            // in meshlets
     swrb_fb* clipCacheFb = nullptr;       // framebuffer the last batch drew into (null = cache unusable)
@@ -260,7 +261,7 @@ void swrb_device_destroy(swrb_device* d) {
     cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
-    cudaFree(d->detileScratch); cudaFree(d->clipCache); cudaFree(d->l2Scratch);
+    cudaFree(d->detileScratch); cudaFree(d->clipCache); cudaFree(d->peerCounter); cudaFree(d->l2Scratch);
     cudaEventDestroy(d->timerBegin); cudaEventDestroy(d->timerEnd);
     if (d->st) {
         for (int s = 0; s < SWRB_STAGE_COUNT_; s++)
@@ -547,6 +548,46 @@ int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uin
 int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream) {
     if (!fb) return fail(SWRB_E_INVALID, "fb is null");
     return get_pixels_device_on(fb, layer, dst_device, stride, (cudaStream_t)cuda_stream);
+}
+
+int swrb_fb_send_pixels(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream, const swrb_peer_sync* sync) {
+    if (!fb || !dst_device || !sync) return fail(SWRB_E_INVALID, "null argument");
+    if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
+    if (stride < fb->width || stride % 4) return fail(SWRB_E_INVALID, "stride %u must be >= width and a multiple of 4", stride);
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    int rc = fb_materialize_for_read(fb, layer);
+    if (rc) return rc;
+    if (!d->peerCounter) {
+        CU(cudaMalloc(&d->peerCounter, 256));
+        CU(cudaMemsetAsync(d->peerCounter, 0, 256, d->stream));
+        CU(cudaStreamSynchronize(d->stream));
+    }
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d->stream;
+    PeerSync ps;
+    ps.waitFlag = reinterpret_cast<const unsigned long long*>(sync->WaitFlag); ps.waitValue = sync->WaitValue;
+    ps.signalFlag = reinterpret_cast<unsigned long long*>(sync->SignalFlag); ps.signalValue = sync->SignalValue;
+    ps.blockCounter = d->peerCounter;
+    // beside the render kernels: one block per SM (see get_pixels_device_on)
+    k_fb_detile_send<<<std::max(1u, (uint32_t)d->numSMs), 256, 0, stream>>>(
+        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride, ps);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+int swrb_peer_collect(swrb_device* d, void* cuda_stream, const uint64_t* ready_flags, uint32_t n, uint64_t expected,
+                      uint64_t* const* ack_flags, uint64_t ack_value) {
+    if (!d || !ready_flags || !ack_flags) return fail(SWRB_E_INVALID, "null argument");
+    if (n == 0 || n > 15) return fail(SWRB_E_INVALID, "n = %u producers: must be in [1, 15]", n);
+    CU(cudaSetDevice(d->cudaDevice));
+    PeerAcks acks;
+    for (uint32_t i = 0; i < 15; i++) acks.flag[i] = i < n ? reinterpret_cast<unsigned long long*>(ack_flags[i]) : nullptr;
+    k_peer_collect<<<1, 32, 0, cuda_stream ? (cudaStream_t)cuda_stream : d->stream>>>(
+        reinterpret_cast<const unsigned long long*>(ready_flags), n, expected, acks, ack_value);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
 }
 
 int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {

@@ -58,13 +58,16 @@ def render_views_sharded(num_views: int, render_view: Callable[[int], "torch.Ten
 
 class PeerComposites:
     """Composite gather without a collective call: every rank's de-tile kernel (Framebuffer::GetPixels) stores
-    its finished view straight into rank 0's buffer through NVLink peer memory.
+    its finished view straight into rank 0's buffer through NVLink peer memory, and the flow control rides in the
+    same kernels (swrb_fb_send_pixels / swrb_peer_collect) instead of separate signal launches.
 
-    The buffer is torch symmetric memory ([slots, world, H, W] int32 on every rank; only rank 0's copy is the
-    gather target). Completion and slot reuse are stream-ordered device-side signals:
-        sender:  wait ack(slot) -> de-tile into root[slot, rank] -> put ready(slot) to rank 0
-        rank 0:  wait ready(slot) from every peer -> (consume) -> put ack(slot) to every peer
-    so no host synchronisation and no NCCL kernel sits on the render stream."""
+    Two symmetric allocations (torch symmetric memory, identical on every rank): the image buffer
+    [slots, world, H, W] int32 (only rank 0's copy is the gather target) and a flag array of uint64 use counts:
+        ready[slot, src]  in rank 0's memory, raised by src's send kernel after its last store (system-scope fence)
+        ack[slot]         in every producer's memory, raised by rank 0's collect kernel when the slot may be reused
+    Per frame a producer launches ONE kernel (wait ack -> de-tile into root[slot, rank] -> raise ready) and rank 0
+    launches its local de-tile plus ONE collect kernel (wait for all ready flags -> raise all acks); no host
+    synchronisation and no kernel on the render stream. Counts only grow, so nothing is reset across the link."""
 
     def __init__(self, height: int, width: int, rank: int, world: int, slots: int = 2):
         import torch
@@ -72,9 +75,17 @@ class PeerComposites:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.rank, self.world, self.slots = rank, world, slots
+        group = dist.group.WORLD.group_name
         self.buf = symm_mem.empty((slots, world, height, width), dtype=torch.int32, device="cuda")
-        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD.group_name)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
         self.root = self.hdl.get_buffer(0, self.buf.shape, self.buf.dtype)   # rank 0's buffer, mapped into this process
+        self.num_flags = slots * world + slots
+        self.flags = symm_mem.empty((self.num_flags,), dtype=torch.int64, device="cuda")
+        self.flags.zero_()
+        self.fhdl = symm_mem.rendezvous(self.flags, group)
+        self.flag_views = [self.fhdl.get_buffer(r, self.flags.shape, self.flags.dtype) for r in range(world)]
+        torch.cuda.synchronize()
+        dist.barrier()                                   # every rank's flags are zero before anyone raises one
         self.uses = [0] * slots
         self.local_ready = [torch.cuda.Event() for _ in range(slots)]
         self.collected = [torch.cuda.Event() for _ in range(slots)]
@@ -82,32 +93,36 @@ class PeerComposites:
     def dst_ptr(self, slot: int) -> int:
         return self.root[slot, self.rank].data_ptr()
 
-    def before_write(self, slot: int, stream):
-        """Sender side, on the render stream: the slot must have been consumed by rank 0."""
-        if self.uses[slot] > 0:
-            if self.rank == 0:
-                stream.wait_event(self.collected[slot])
-            else:
-                self.hdl.wait_signal(0, channel=self.slots + slot)
+    def ready_ptr(self, slot: int, src: int) -> int:
+        """ready[slot, src] in rank 0's memory."""
+        return self.flag_views[0].data_ptr() + 8 * (slot * self.world + src)
+
+    def ack_ptr(self, slot: int, owner: int) -> int:
+        """ack[slot] in `owner`'s memory."""
+        return self.flag_views[owner].data_ptr() + 8 * (self.slots * self.world + slot)
+
+    def send(self, fb, slot: int, comm_stream, layer: int = 0):
+        """This rank's finished view -> root[slot, rank], on `comm_stream`. Returns the use count of the slot."""
         self.uses[slot] += 1
-
-    def after_write(self, slot: int, stream):
+        n = self.uses[slot]
         if self.rank == 0:
-            self.local_ready[slot].record(stream)
+            if n > 1:
+                comm_stream.wait_event(self.collected[slot])
+            fb.get_pixels_device(layer, self.dst_ptr(slot), cuda_stream=comm_stream.cuda_stream)
+            self.local_ready[slot].record(comm_stream)
         else:
-            self.hdl.put_signal(0, channel=slot)
+            fb.send_pixels(layer, self.dst_ptr(slot), comm_stream.cuda_stream,
+                           wait_flag=self.ack_ptr(slot, self.rank) if n > 1 else 0, wait_value=n - 1,
+                           signal_flag=self.ready_ptr(slot, self.rank), signal_value=n)
+        return n
 
-    def collect(self, slot: int, comm_stream):
-        """Rank 0, on a side stream: wait for every view of this slot, then release the slot."""
-        import torch
+    def collect(self, rast, slot: int, coll_stream):
+        """Rank 0, on a side stream: wait for every view of this use of the slot, then release the slot."""
         if self.rank != 0:
             return None
-        with torch.cuda.stream(comm_stream):
-            comm_stream.wait_event(self.local_ready[slot])
-            for src in range(1, self.world):
-                self.hdl.wait_signal(src, channel=slot)
-            views = self.buf[slot]                   # [world, H, W] — all composites of this round
-            for src in range(1, self.world):
-                self.hdl.put_signal(src, channel=self.slots + slot)
-            self.collected[slot].record(comm_stream)
-        return views
+        coll_stream.wait_event(self.local_ready[slot])
+        if self.world > 1:
+            rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, self.uses[slot],
+                              [self.ack_ptr(slot, r) for r in range(1, self.world)], self.uses[slot])
+        self.collected[slot].record(coll_stream)
+        return self.buf[slot]                   # [world, H, W] — all composites of this round

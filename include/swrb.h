@@ -118,6 +118,21 @@ SWRB_API int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_de
  * dst may be peer memory of another GPU: the de-tile kernel then stores straight over NVLink. */
 SWRB_API int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream);
 
+/* Multi-GPU composite exchange (no reference counterpart: the reference is one process). GetPixels whose
+ * destination is another GPU's memory (NVLink peer mapping) with the flow control folded into the same kernel:
+ * it first waits until *WaitFlag >= WaitValue (a flag in THIS GPU's memory that the consumer raises when the
+ * destination slot may be overwritten; NULL = no wait) and, after its last store, sets *SignalFlag = SignalValue
+ * (a flag in the CONSUMER's memory; NULL = no signal) behind a system-scope fence. Runs on `cuda_stream`. */
+typedef struct swrb_peer_sync {
+    const uint64_t* WaitFlag;   uint64_t WaitValue;
+    uint64_t*       SignalFlag; uint64_t SignalValue;
+} swrb_peer_sync;
+SWRB_API int swrb_fb_send_pixels(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream, const swrb_peer_sync* sync);
+/* Consumer side: one small kernel on `cuda_stream` that waits until ready_flags[0..n) (this GPU's memory) are all
+ * >= expected, then stores ack_value to each of ack_flags[0..n) (the producers' memories). n <= 15. */
+SWRB_API int swrb_peer_collect(swrb_device* dev, void* cuda_stream, const uint64_t* ready_flags, uint32_t n, uint64_t expected,
+                               uint64_t* const* ack_flags, uint64_t ack_value);
+
 /* ---- hot path ------------------------------------------------------------------------ */
 /* ShadingContext::CullMeshlets frustum part (Shading.cpp:775-809, :865-867). Planes are
  * derived on the host from P,V,M exactly as the reference does (the HiZ half is

@@ -39,15 +39,14 @@ def _worker(rank, world, port, q):
         fb.clear(0xFF000000 + k, 0.0)
         rast.draw_meshlets(fb, gscene, node.meshlet_offset, node.meshlet_count, scene.object_to_clip(node))
         rast.resolve(fb, gscene, **uni)
-        peers.before_write(slot, stream)
-        fb.get_pixels_device(0, peers.dst_ptr(slot))
-        peers.after_write(slot, stream)
-        views = peers.collect(slot, comm)
+        peers.send(fb, slot, stream)               # rank 1: ONE kernel = wait for the slot's ack, de-tile over NVLink, raise ready
+        views = peers.collect(rast, slot, comm)    # rank 0: ONE kernel = wait for rank 1's ready flag, ack the slot
         local = fb.get_pixels(0)
         sums.append(int(local.astype(np.uint64).sum()))
         if rank == 0:
             comm.synchronize()
             got.append([int(views[r].cpu().numpy().view(np.uint32).astype(np.uint64).sum()) for r in range(world)])
+        dist.barrier()                             # rank 0 has read the slot before anyone may overwrite it (the ack is already out)
     all_sums = [None] * world
     dist.all_gather_object(all_sums, sums)
     torch.cuda.synchronize()
