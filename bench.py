@@ -116,6 +116,28 @@ def algorithmic_bytes(scene):
     return {"mesh": 16 * m_tested + 1216 * m_visible, "raster": 8 * px, "resolve": 12 * px}
 
 
+def bind_to_gpu_numa_node(gpu_index: int) -> None:
+    """Pins this rank (and with it the pinned host buffers it allocates) to the CPU socket its GPU hangs off, so that
+    the e2e copies of 8 ranks do not all cross the inter-socket link. Best effort: silently does nothing when the
+    topology cannot be read."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out                      # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -126,6 +148,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner under
     # NCCL_DEBUG=VERSION, ...) is routed to stderr until the line is written

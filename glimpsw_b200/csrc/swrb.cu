@@ -568,7 +568,8 @@ int swrb_fb_send_pixels(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t 
     ps.waitFlag = reinterpret_cast<const unsigned long long*>(sync->WaitFlag); ps.waitValue = sync->WaitValue;
     ps.signalFlag = reinterpret_cast<unsigned long long*>(sync->SignalFlag); ps.signalValue = sync->SignalValue;
     ps.blockCounter = d->peerCounter;
-    // beside the render kernels: one block per SM (see get_pixels_device_on)
+    // beside the render kernels: one block per SM; measured insensitive to the grid size between 32 and 148 blocks
+    // (stores over NVLink are posted, a few hundred KB in flight keep the link busy)
     k_fb_detile_send<<<std::max(1u, (uint32_t)d->numSMs), 256, 0, stream>>>(
         reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride, ps);
     d->launches++;
