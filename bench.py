@@ -7,8 +7,8 @@ Rasterizer::DrawMeshlets (vis-buffer) -> ShadingContext::Resolve, i.e. BASELINE.
 (procedural 999,600-triangle meshlet grid, 1920x1080) bound to a procedural two-layer material so the
 resolve pass samples textures.
 
-  value   whole-job throughput, scene resident in HBM: K frames submitted round-robin to F (default 3)
-          independent render contexts (own stream, framebuffer, work buffers) so that the issue-bound resolve
+  value   whole-job throughput, scene resident in HBM: K frames submitted round-robin to F (default 5)
+          independent render contexts (own stream, framebuffer, work buffers; mesh kernel sized to half of each SM) so that the issue-bound resolve
           of one frame overlaps the latency-bound mesh/raster kernels of the next. Inputs are larger than L2:
           the contexts rotate over 8 copies of the 17.6 MB meshlet buffer (141 MB > 126 MB L2), so no frame
           finds its meshlets cached. Timed with CUDA events on the launching streams; max over ranks.
@@ -49,7 +49,7 @@ from glimpsw_b200.layout import MATERIAL_DTYPE  # noqa: E402
 METRIC = "Mtri/s @1080p vis-buffer+resolve"
 UNIT = "Mtri/s"
 SCENE_COPIES = 8          # x 17.6 MB of meshlets = 141 MB > 126 MB L2
-SLOTS = 4                 # N > 1: composite buffers in flight per rank
+SLOTS = 6                 # N > 1: composite buffers in flight per rank
 
 
 def build_workload(rank: int = 0):
@@ -174,6 +174,7 @@ def run_ours(args):
         st = torch.cuda.Stream()
         assert st.cuda_stream != 0
         r.set_stream(st.cuda_stream)
+        r.set_mesh_occupancy(args.mesh_blocks if F > 1 else 4)     # several contexts in flight: leave half of each SM to the others' resolve
         c = SimpleNamespace(rast=r, stream=st, fb=r.create_framebuffer(scene.width, scene.height),
                             scenes=[r.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights) for _ in range(copies)],
                             batch=r.make_batch([dict(offset=node.meshlet_offset, count=node.meshlet_count,
@@ -283,6 +284,7 @@ def run_ours(args):
     # ---- latency mode: one context, strictly serial, L2 evicted before every frame; per-stage times for the roofline
     c0 = ctxs[0]
     rast = c0.rast
+    rast.set_mesh_occupancy(4)                                    # a lone frame gets the whole register file
     lat_steps = min(args.steps, 100)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(lat_steps)]
     save_exchange, exchange = exchange, False
@@ -344,14 +346,16 @@ def run_ours(args):
     if roofline["traffic"] is not None:
         roofline["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
 
-    # ---- e2e: the same frames through the C ABI with HOST buffers, F steps in flight
-    for c in ctxs:
+    # ---- e2e: the same frames through the C ABI with HOST buffers; PCIe-bound, and more than 3 steps in flight only
+    # add copy-engine contention (tools/e2e_probe.py), so at most 3 of the contexts take part
+    FE = min(F, 3)
+    for c in ctxs[:FE]:
         c.host_meshlets = c.rast.alloc_pinned(scene.meshlets.shape, scene.meshlets.dtype)
         c.host_meshlets[...] = scene.meshlets
         c.host_image = c.rast.alloc_pinned((scene.height, scene.width), np.uint32)
 
     def frame_e2e(k):
-        c = ctxs[k % F]
+        c = ctxs[k % FE]
         if c.uses >= 1:
             c.rast.sync()                                         # this context's previous step (its image is now on the host)
         c.uses += 1
@@ -362,7 +366,7 @@ def run_ours(args):
         c.rast.resolve_prebuilt(c.fb, g, uni_c)
         c.fb.get_pixels_async(0, c.host_image)                    # D2H: resolved RGBA8 image
 
-    for k in range(3 * F):
+    for k in range(3 * FE):
         frame_e2e(k)
     barrier()
     t0e = time.perf_counter()
@@ -390,7 +394,7 @@ def run_ours(args):
             "config": {"workload": "C2: procedural 999,600-triangle meshlet grid (10,200 meshlets), 1920x1080, "
                                    "clear + vis-buffer (depth + triangle id) + resolve (1 material, 1024^2 2-layer texture, 1 directional light)",
                        "triangles_per_frame": tris, "meshlets": len(scene.meshlets), "mode": args.mode,
-                       "frames_in_flight": F,
+                       "frames_in_flight": F, "mesh_kernel_blocks_per_sm": args.mesh_blocks if F > 1 else 4,
                        "parallelism": f"view-parallel x{world}" + {
                            "p2p": ", composites stored by each rank's de-tile kernel straight into rank 0's memory over NVLink (peer memory + device-side signals, double-buffered, tail included)",
                            "nccl": ", composites gathered to rank 0 with NCCL on a side stream (double-buffered, tail included)", "none": ""}[gather_kind],
@@ -405,7 +409,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(scene.meshlets.nbytes + 512),
                     "d2h_bytes_per_step": int(scene.width * scene.height * 4), "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "note": f"every step: meshlets H2D from pinned host memory, draw + resolve, resolved image D2H to pinned host memory; "
-                            f"{F} steps in flight on separate streams; wall clock"},
+                            f"{FE} steps in flight on separate streams; wall clock"},
             "roofline": roofline, "stages": stages,
             "counters": {k: counters[k] for k in ("TrianglesProcessed", "TrianglesRasterized", "TrianglesClipped", "BinQueueFlushes")},
             "draw_stats": draw_stats, "image_xor": checksum,
@@ -506,7 +510,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="binned", choices=["binned", "direct"])
-    ap.add_argument("--in-flight", type=int, default=3, help="independent render contexts (frames in flight) per GPU")
+    ap.add_argument("--in-flight", type=int, default=5, help="independent render contexts (frames in flight) per GPU")
+    ap.add_argument("--mesh-blocks", type=int, default=2, help="mesh-kernel blocks per SM in the sustained mode (swrb_device_set_mesh_occupancy)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -51,7 +51,7 @@ EXPORTS = [
     "swrb_alloc_pinned", "swrb_free_pinned", "swrb_get_draw_stats", "swrb_fb_get_pixels_device_on_stream",
     "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
     "swrb_hiz_download", "swrb_cull_meshlets_hiz", "swrb_draw_batch_program", "swrb_resolve_debug",
-    "swrb_fb_send_pixels", "swrb_peer_collect",
+    "swrb_fb_send_pixels", "swrb_peer_collect", "swrb_device_set_mesh_occupancy",
 ]
 
 PROGRAM_VISBUFFER, PROGRAM_OVERDRAW = 0, 1     # ShadingContext::VisBufferShader / OverdrawShader (Shading.h:49)
@@ -294,6 +294,10 @@ class Rasterizer:
                       (FLAG_GUARDBAND if enable_guardband else 0) | (FLAG_FUSED_FRUSTUM_CULL if fused_frustum_cull else 0) |
                       (0 if resolve_cache else FLAG_NO_RESOLVE_CACHE))
         _check(self.lib.swrb_device_set_flags(self._h, C.c_uint32(self.flags)))
+
+    def set_mesh_occupancy(self, blocks_per_sm: int):
+        """Persistent-grid size of the mesh kernel (1..4 blocks per SM; 2 suits several contexts in flight)."""
+        _check(self.lib.swrb_device_set_mesh_occupancy(self._h, C.c_uint32(blocks_per_sm)))
 
     def set_stream(self, cuda_stream: int | None):
         _check(self.lib.swrb_device_set_stream(self._h, C.c_void_p(cuda_stream or 0)))

@@ -118,6 +118,7 @@ struct swrb_device {
     // Per-vertex {x/w, y/w, 1/w, z/w} of the last batch, written by the mesh kernel for the resolve pass.
     // swrb_resolve may read it only if every surface id in the framebuffer provably comes from that batch
     // and the batch used the one matrix the resolve is handed (see clip_cache_usable).
+    uint32_t meshBlocksPerSM = 4;         // persistent grid of the mesh kernel (swrb_device_set_mesh_occupancy)
     uint32_t* peerCounter = nullptr;      // block counter of k_fb_detile_send (multi-GPU composite exchange)
     float4* clipCache = nullptr;
     uint64_t clipCacheCap = 0;            // in meshlets
@@ -310,6 +311,13 @@ int swrb_get_counters(swrb_device* d, uint64_t out[SWR_PERF_Count_]) {
     if (rc) return rc;
     for (int i = 0; i < 4; i++) out[i] = d->ctlHost->perf[i];
     for (int i = 4; i < SWR_PERF_Count_; i++) out[i] = d->hostTimeNs[i];
+    return SWRB_OK;
+}
+
+int swrb_device_set_mesh_occupancy(swrb_device* d, uint32_t blocks_per_sm) {
+    if (!d) return fail(SWRB_E_INVALID, "device is null");
+    if (blocks_per_sm < 1 || blocks_per_sm > 4) return fail(SWRB_E_INVALID, "blocks_per_sm = %u: must be in [1, 4]", blocks_per_sm);
+    d->meshBlocksPerSM = blocks_per_sm;
     return SWRB_OK;
 }
 
@@ -1015,7 +1023,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         d->launches++;
     }
 
-    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, 4);      // 64 registers -> 4 resident blocks per SM
+    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, d->meshBlocksPerSM);   // 64 registers -> at most 4 resident blocks per SM
     // record consumers are grid-stride loops over a device-side count; size their grids from the last count
     // the host has seen (any grid is correct, a fitting one avoids launching a thousand idle blocks)
     const uint64_t recEstimate = std::min<uint64_t>(d->triCap, std::max<uint64_t>(4096, 4 * (uint64_t)d->lastTriCount));

@@ -82,6 +82,11 @@ SWRB_API int swrb_device_create(int cuda_device, swrb_device** out);   /* Raster
 SWRB_API void swrb_device_destroy(swrb_device* dev);
 SWRB_API int swrb_device_set_stream(swrb_device* dev, void* cuda_stream); /* borrow an external cudaStream_t (NULL = own) */
 SWRB_API int swrb_device_set_flags(swrb_device* dev, uint32_t flags);  /* EnableBinning/Clipping/Guardband */
+/* Size of the mesh kernel's persistent grid in blocks (of 8 warps) per SM, 1..4, default 4. A lone frame is fastest with
+ * the whole register file (4); a caller that keeps several render contexts in flight on one GPU gets more frames per
+ * second with 2: the mesh kernel then leaves half of every SM to the other contexts' resolve blocks, and the
+ * latency-bound mesh warps and the issue-bound resolve warps fill each other's idle issue slots. */
+SWRB_API int swrb_device_set_mesh_occupancy(swrb_device* dev, uint32_t blocks_per_sm);
 SWRB_API int swrb_device_reserve(swrb_device* dev, uint64_t max_triangles, uint64_t max_bin_entries);
 SWRB_API int swrb_sync(swrb_device* dev);
 SWRB_API const char* swrb_last_error(void);
