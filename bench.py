@@ -7,8 +7,8 @@ Rasterizer::DrawMeshlets (vis-buffer) -> ShadingContext::Resolve, i.e. BASELINE.
 (procedural 999,600-triangle meshlet grid, 1920x1080) bound to a procedural two-layer material so the
 resolve pass samples textures.
 
-  value   whole-job throughput, scene resident in HBM: K frames submitted round-robin to F (default 5)
-          independent render contexts (own stream, framebuffer, work buffers; mesh kernel sized to half of each SM) so that the issue-bound resolve
+  value   whole-job throughput, scene resident in HBM: K frames submitted round-robin to F (default 6)
+          independent render contexts (own stream, framebuffer, work buffers; mesh kernel sized to one block per SM) so that the issue-bound resolve
           of one frame overlaps the latency-bound mesh/raster kernels of the next. Inputs are larger than L2:
           the contexts rotate over 8 copies of the 17.6 MB meshlet buffer (141 MB > 126 MB L2), so no frame
           finds its meshlets cached. Timed with CUDA events on the launching streams; max over ranks.
@@ -510,8 +510,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="binned", choices=["binned", "direct"])
-    ap.add_argument("--in-flight", type=int, default=5, help="independent render contexts (frames in flight) per GPU")
-    ap.add_argument("--mesh-blocks", type=int, default=2, help="mesh-kernel blocks per SM in the sustained mode (swrb_device_set_mesh_occupancy)")
+    ap.add_argument("--in-flight", type=int, default=6, help="independent render contexts (frames in flight) per GPU")
+    ap.add_argument("--mesh-blocks", type=int, default=1, help="mesh-kernel blocks per SM in the sustained mode (swrb_device_set_mesh_occupancy)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1195,9 +1195,9 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
     rp.debugLayer = debugLayer;
     if (debugLayer != SWRB_LAYER_NONE) {            // ResolveDebug: surface only, no lighting, no light markers
         StageScope ss(d, SWRB_STAGE_RESOLVE);
-        dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
-        if (fromKeys) k_resolve<true, false, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
-        else k_resolve<false, false, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        dim3 grid((fb->width + 31) / 32, (fb->height + 3) / 4), block(32, kResolveWarps);
+        if (fromKeys) k_resolve<true, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
+        else k_resolve<false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
         d->launches++;
         if (fromKeys) fb->layer0IsColor = true;
         CU(cudaGetLastError());
@@ -1205,10 +1205,12 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
     }
     {
         StageScope ss(d, SWRB_STAGE_RESOLVE);
-        dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
-        if (cached) k_resolve<true, true><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
-        else if (fromKeys) k_resolve<true, false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
-        else k_resolve<false, false><<<grid, dim3(32, 8), 0, d->stream>>>(rp, d->ctl);
+        // 4 warps = 32 x 4 pixels per block: small blocks pack better beside other contexts' mesh blocks (measured +2 %
+        // frames/s over 8-warp blocks, same single-frame time)
+        dim3 grid((fb->width + 31) / 32, (fb->height + 3) / 4), block(32, kResolveWarps);
+        if (cached) k_resolve<true, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
+        else if (fromKeys) k_resolve<true, false><<<grid, block, 0, d->stream>>>(rp, d->ctl);
+        else k_resolve<false, false><<<grid, block, 0, d->stream>>>(rp, d->ctl);
         d->launches++;
     }
     // Tail of Resolve (Shading.cpp:690-731): point / spot lights inside the frustum become soft discs, in light order.
