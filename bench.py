@@ -48,6 +48,8 @@ from glimpsw_b200.layout import MATERIAL_DTYPE  # noqa: E402
 
 METRIC = "Mtri/s @1080p vis-buffer+resolve"
 UNIT = "Mtri/s"
+WORKLOAD = ("C2: procedural 999,600-triangle meshlet grid (10,200 meshlets), 1920x1080, "
+            "clear + vis-buffer (depth + triangle id) + resolve (1 material, 1024^2 2-layer texture, 1 directional light)")
 SCENE_COPIES = 8          # x 17.6 MB of meshlets = 141 MB > 126 MB L2
 SLOTS = 6                 # N > 1: composite buffers in flight per rank
 
@@ -391,8 +393,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+i32 (28.4 fixed-point coverage, fp32 depth/shading)", "data": "synthetic",
-            "config": {"workload": "C2: procedural 999,600-triangle meshlet grid (10,200 meshlets), 1920x1080, "
-                                   "clear + vis-buffer (depth + triangle id) + resolve (1 material, 1024^2 2-layer texture, 1 directional light)",
+            "config": {"workload": WORKLOAD,
                        "triangles_per_frame": tris, "meshlets": len(scene.meshlets), "mode": args.mode,
                        "frames_in_flight": F, "mesh_kernel_blocks_per_sm": args.mesh_blocks if F > 1 else 4,
                        "parallelism": f"view-parallel x{world}" + {
@@ -495,7 +496,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+i32", "data": "synthetic",
-        "config": {"workload": "C2: procedural 999,600-triangle meshlet grid, 1920x1080, clear + vis-buffer + resolve",
+        "config": {"workload": WORKLOAD, "triangles_per_frame": scene.num_triangles, "meshlets": len(scene.meshlets),
                    "note": "CPU restatement of GLimpSW's binned AVX-512 path (oracle/baseline_mt.cpp); the upstream binary needs clang + CPM deps and cannot be built here"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
