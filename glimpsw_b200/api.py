@@ -52,6 +52,7 @@ EXPORTS = [
     "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
     "swrb_hiz_download", "swrb_cull_meshlets_hiz", "swrb_draw_batch_program", "swrb_resolve_debug",
     "swrb_fb_send_pixels", "swrb_peer_collect", "swrb_device_set_mesh_occupancy",
+    "swrb_scene_set_skybox",
 ]
 
 PROGRAM_VISBUFFER, PROGRAM_OVERDRAW = 0, 1     # ShadingContext::VisBufferShader / OverdrawShader (Shading.h:49)
@@ -223,6 +224,20 @@ class Scene:
                                           _ptr(lights) if len(lights) else None, C.c_uint32(len(lights)),
                                           C.byref(self._h)))
         rast._children.add(self)
+
+    def set_skybox(self, tex):
+        """ShadingContext::SkyboxTex: an octahedron-mapped Texture2D<R11G11B10f> (textures.procedural_sky_texture); None removes it."""
+        if tex is None:
+            _check(self.rast.lib.swrb_scene_set_skybox(self._h, None))
+            return
+        data = np.ascontiguousarray(tex.data, dtype=np.uint32)
+        d = TextureDesc()
+        d.Width, d.Height, d.MipLevels, d.NumLayers = tex.width, tex.height, tex.mip_levels, tex.num_layers
+        d.RowShift, d.LayerStride = tex.row_shift, tex.layer_stride
+        for k in range(16):
+            d.MipOffsets[k] = int(tex.mip_offsets[k])
+        d.Data = data.ctypes.data
+        _check(self.rast.lib.swrb_scene_set_skybox(self._h, C.byref(d)))
 
     def update_meshlets(self, meshlets: np.ndarray, first: int = 0):
         meshlets = np.ascontiguousarray(meshlets)

@@ -142,6 +142,8 @@ struct swrb_scene {
     ResolveTexture* textures = nullptr;   // device table
     std::vector<uint32_t*> textureData;
     uint32_t numTextures = 0;
+    ResolveTexture sky = {};              // ShadingContext::SkyboxTex (swrb_scene_set_skybox); skyData == nullptr: none
+    uint32_t* skyData = nullptr;
     float4* attr = nullptr;               // resolve-pass attribute table (k_decode_attributes), 2 float4 per vertex
     uint32_t attrDirtyLo = 0, attrDirtyHi = 0;   // meshlet range whose attributes must be (re)decoded before the next resolve
     swr_light* lights = nullptr;
@@ -396,12 +398,33 @@ int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint3
     return SWRB_OK;
 }
 
+int swrb_scene_set_skybox(swrb_scene* s, const swr_texture_desc* hdr) {
+    if (!s) return fail(SWRB_E_INVALID, "scene is null");
+    swrb_device* d = s->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    CU(cudaStreamSynchronize(d->stream));            // a resolve in flight may still be sampling the old skybox
+    if (s->skyData) { CU(cudaFree(s->skyData)); s->skyData = nullptr; }
+    if (!hdr) return SWRB_OK;
+    if (!hdr->Data || hdr->Width < 8 || hdr->Height < 8 || (hdr->Width & (hdr->Width - 1)) || (hdr->Height & (hdr->Height - 1)) || hdr->MipLevels < 1 || hdr->MipLevels > 16)
+        return fail(SWRB_E_INVALID, "skybox must be a power-of-two Texture2D<R11G11B10f> of at least 8x8 texels with 1..16 mip levels");
+    const size_t texels = (size_t)hdr->LayerStride * std::max(1u, hdr->NumLayers);
+    CU(cudaMalloc(&s->skyData, texels * 4 + 256));
+    CU(cudaMemcpyAsync(s->skyData, hdr->Data, texels * 4, cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));            // the host texels are only borrowed for the call
+    ResolveTexture& r = s->sky;
+    r.data = s->skyData;
+    r.width = hdr->Width; r.height = hdr->Height; r.mipLevels = hdr->MipLevels; r.numLayers = hdr->NumLayers;
+    r.rowShift = hdr->RowShift; r.layerStride = hdr->LayerStride;
+    for (int m = 0; m < 16; m++) r.mipOffsets[m] = hdr->MipOffsets[m];
+    return SWRB_OK;
+}
+
 void swrb_scene_destroy(swrb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->dev->cudaDevice);
     cudaStreamSynchronize(s->dev->stream);
     if (s->dev->clipCacheMeshlets == s->meshlets) s->dev->clipCacheFb = nullptr;
-    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights); cudaFree(s->attr);
+    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights); cudaFree(s->attr); cudaFree(s->skyData);
     for (uint32_t* p : s->textureData) cudaFree(p);
     delete s;
 }
@@ -1208,9 +1231,11 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
         // 4 warps = 32 x 4 pixels per block: small blocks pack better beside other contexts' mesh blocks (measured +2 %
         // frames/s over 8-warp blocks, same single-frame time)
         dim3 grid((fb->width + 31) / 32, (fb->height + 3) / 4), block(32, kResolveWarps);
-        if (cached) k_resolve<true, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
-        else if (fromKeys) k_resolve<true, false><<<grid, block, 0, d->stream>>>(rp, d->ctl);
-        else k_resolve<false, false><<<grid, block, 0, d->stream>>>(rp, d->ctl);
+        const bool sky = scene->skyData != nullptr;
+        if (sky) rp.sky = scene->sky;
+        if (cached) { if (sky) k_resolve<true, true, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<true, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); }
+        else if (fromKeys) { if (sky) k_resolve<true, false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<true, false><<<grid, block, 0, d->stream>>>(rp, d->ctl); }
+        else { if (sky) k_resolve<false, false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<false, false><<<grid, block, 0, d->stream>>>(rp, d->ctl); }
         d->launches++;
     }
     // Tail of Resolve (Shading.cpp:690-731): point / spot lights inside the frustum become soft discs, in light order.

@@ -107,3 +107,62 @@ def procedural_material_texture(size: int = 1024, seed: int = 0, with_nmr: bool 
         set_pixels(tex, pack_rgba(nx, ny, metal, rough), 1)
     generate_mips(tex)
     return tex
+
+
+# ---- HdrTexture2D = Texture2D<R11G11B10f, TiledY8> (Texture.h:133-200, :216): the skybox of ShadingContext::Resolve ----
+def pack_r11g11b10f(r, g, b) -> np.ndarray:
+    """pixfmt::R11G11B10f::Pack (Texture.h:145-167): clamp to [2^-15, max], truncate the mantissa."""
+    def f11(x):
+        x = np.minimum(np.maximum(np.asarray(x, dtype=f32), f32(1.0 / (1 << 15))), f32(130048.0))
+        return ((x.view(np.uint32) >> 17) & 0x3FFF) - 0x1C00
+    def f10(x):
+        x = np.minimum(np.maximum(np.asarray(x, dtype=f32), f32(1.0 / (1 << 15))), f32(129024.0))
+        return ((x.view(np.uint32) >> 18) & 0x1FFF) - 0x0E00
+    return (f11(r).astype(np.uint32) << 21) | (f11(g).astype(np.uint32) << 10) | f10(b).astype(np.uint32)
+
+
+def unpack_r11g11b10f(p: np.ndarray):
+    """pixfmt::R11G11B10f::Unpack (Texture.h:138-144, :170-182)."""
+    p = np.asarray(p, dtype=np.uint32)
+    r = ((((p >> 21) << 17) & 0x0FFE0000) + 0x38000000).astype(np.uint32).view(f32)
+    g = ((((p >> 10) << 17) & 0x0FFE0000) + 0x38000000).astype(np.uint32).view(f32)
+    b = (((p << 18) & 0x0FFC0000) + 0x38000000).astype(np.uint32).view(f32)
+    return r, g, b
+
+
+def generate_mips_hdr(tex: TextureData):
+    """Texture2D<R11G11B10f>::GenerateMip (Texture.h:577-596): unpack, (((a+b)+c)+d)*0.25 in float32, pack (truncating)."""
+    for level in range(1, tex.mip_levels):
+        src = get_pixels(tex, 0, level - 1)
+        ch = unpack_r11g11b10f(src)
+        avg = [(((c[0::2, 0::2] + c[0::2, 1::2]) + c[1::2, 0::2]) + c[1::2, 1::2]) * f32(0.25) for c in ch]
+        set_pixels(tex, pack_r11g11b10f(*avg), 0, level)
+
+
+def unmap_octahedron(u: np.ndarray, v: np.ndarray):
+    """texutil::UnmapOctahedron (Texture.h:289-296), float64: texel centre -> direction."""
+    x, y = u * 2.0 - 1.0, v * 2.0 - 1.0
+    z = 1.0 - np.abs(x) - np.abs(y)
+    t = np.maximum(-z, 0.0)
+    x, y = x - np.copysign(t, x), y - np.copysign(t, y)
+    n = np.sqrt(x * x + y * y + z * z)
+    return x / n, y / n, z / n
+
+
+def procedural_sky_texture(size: int = 256, sun_dir=(0.4, 0.7, 0.6), max_levels: int = 6) -> TextureData:
+    """An octahedron-mapped HDR sky (stand-in for the reference's panorama -> octahedron import, the HDR files are not in
+    the checkout): horizon-to-zenith gradient, a ground tint and an HDR sun lobe well above 1.0."""
+    tex = create_texture(size, size, max_levels, 1)
+    v, u = np.meshgrid((np.arange(size) + 0.5) / size, (np.arange(size) + 0.5) / size, indexing="ij")
+    x, y, z = unmap_octahedron(u, v)
+    s = np.asarray(sun_dir, dtype=np.float64)
+    s = s / np.linalg.norm(s)
+    up = np.clip(y, 0.0, 1.0)
+    sun = np.clip(x * s[0] + y * s[1] + z * s[2], 0.0, 1.0) ** 64
+    ground = (y < 0).astype(np.float64)
+    r = 0.55 - 0.35 * up + 12.0 * sun - 0.35 * ground
+    g = 0.70 - 0.25 * up + 10.0 * sun - 0.45 * ground
+    b = 0.95 - 0.10 * up + 7.0 * sun - 0.70 * ground
+    set_pixels(tex, pack_r11g11b10f(np.maximum(r, 0.02), np.maximum(g, 0.02), np.maximum(b, 0.02)), 0)
+    generate_mips_hdr(tex)
+    return tex

@@ -104,6 +104,9 @@ public:
                                 (uint32_t)textures.size(), lights, numLights, &_scene));
     }
 
+    // ShadingContext::SkyboxTex = tex (Shading.h:29, Main.cpp:186): an octahedron-mapped HdrTexture2D; nullptr removes it
+    void SetSkybox(const swr_texture_desc* hdrTexture) { check(swrb_scene_set_skybox(_scene, hdrTexture)); }
+
     // ShadingContext::CullMeshlets(bitmap, meshlets + offset, count, P, V, M, prevV, frameSize, depthMap) — Shading.cpp:775
     template <class Mat4>
     uint32_t CullMeshlets(uint16_t* bitmap, uint32_t meshletOffset, uint32_t count, const Mat4& proj, const Mat4& view, const Mat4& model,

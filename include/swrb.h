@@ -104,6 +104,11 @@ SWRB_API int swrb_scene_create(swrb_device* dev,
                                const swr_light* lights, uint32_t num_lights,
                                swrb_scene** out);
 SWRB_API int swrb_scene_update_meshlets(swrb_scene* scene, const swr_meshlet* meshlets, uint32_t first, uint32_t count);
+/* ShadingContext::SkyboxTex (Shading.h:29, Main.cpp:186): an HdrTexture2D = Texture2D<pixfmt::R11G11B10f> in the reference's
+ * TiledY8 storage with its mip chain (Texture.h:133-200, :216), octahedron-mapped. With a skybox set, swrb_resolve gives sky
+ * pixels SkyboxTex->SampleOctLevel<EnvSampler>(worldPos - ViewPos, 1) (Shading.cpp:676-679) instead of colour 0.
+ * NULL removes it. The texels are copied; the pointer is only borrowed for the call. */
+SWRB_API int swrb_scene_set_skybox(swrb_scene* scene, const swr_texture_desc* hdr_texture);
 SWRB_API void swrb_scene_destroy(swrb_scene* scene);
 
 /* ---- framebuffer (CreateFramebuffer Rasterizer.h:66-78; Clear/ClearLayer :35-48;

@@ -144,6 +144,50 @@ inline uint32_t sample_level(const swr_texture_desc& t, float u, float v, uint32
     return rbCol | (gaCol << 8);
 }
 
+// pixfmt::R11G11B10f::Unpack — Texture.h:138-144, :170-182 (5-bit exponent, 6 / 5-bit mantissa, no denormals)
+inline void unpack_r11g11b10f(uint32_t p, float out[3]) {
+    out[0] = u2f((((p >> 21) << 17) & 0x0FFE0000u) + 0x38000000u);
+    out[1] = u2f((((p >> 10) << 17) & 0x0FFE0000u) + 0x38000000u);
+    out[2] = u2f(((p << 18) & 0x0FFC0000u) + 0x38000000u);
+}
+
+// texutil::MapOctahedron — Texture.h:282-288
+inline void map_octahedron(V3 n, float& u, float& v) {
+    float w = approx_rcp(std::fabs(n.x) + std::fabs(n.y) + std::fabs(n.z));
+    float t = std::fmax(-n.z * w, 0.0f);
+    u = std::fmaf(n.x, w, mulsign(t, n.x)) * 0.5f + 0.5f;
+    v = std::fmaf(n.y, w, mulsign(t, n.y)) * 0.5f + 0.5f;
+}
+
+// HdrTexture2D::SampleOctLevel<EnvSampler>(dir, 1) — Texture.h:467-480 with SampleLevel<ClampToEdge, Linear, Linear>
+// (:412-459) and the float branch of SampleLinear (:557-573). mipLevel = 1.0 exactly: baseMip = 1, mipFrac = 0, so one
+// bilinear sample of level 1 (`any(mipLevel > 0)` selects MinFilter = Linear; the level is clamped to the chain).
+inline void sample_skybox(const swr_texture_desc& t, V3 dir, float out[3]) {
+    float u, v;
+    map_octahedron(dir, u, v);
+    const int32_t maskLerpU = (int32_t)(t.Width << 8) - 1, maskLerpV = (int32_t)(t.Height << 8) - 1;
+    int32_t ix = round2i(u * (float)(maskLerpU + 1)), iy = round2i(v * (float)(maskLerpV + 1));
+    ix = ix < 0 ? 0 : (ix > maskLerpU ? maskLerpU : ix);                      // ClampToEdge (:421-423)
+    iy = iy < 0 ? 0 : (iy > maskLerpV ? maskLerpV : iy);
+    int32_t maxLevel = (int32_t)t.MipLevels - 1, mipLevel = 1 > maxLevel ? maxLevel : 1;
+    uint32_t offset = 0, stride = t.RowShift;
+    if (mipLevel > 0) { ix >>= mipLevel; iy >>= mipLevel; stride -= (uint32_t)mipLevel; offset += t.MipOffsets[mipLevel]; }
+    int32_t ixf = ix - 127 > 0 ? ix - 127 : 0, iyf = iy - 127 > 0 ? iy - 127 : 0;
+    int32_t tx = ixf >> 8, ty = iyf >> 8;
+    bool inboundX = ((tx + 1) << mipLevel) < (int32_t)t.Width, inboundY = ((ty + 1) << mipLevel) < (int32_t)t.Height;
+    uint32_t i00 = offset + texel_offset((uint32_t)tx, (uint32_t)ty, stride);
+    uint32_t i01 = offset + texel_offset((uint32_t)tx, (uint32_t)(ty + (inboundY ? 1 : 0)), stride);
+    float c00[3], c10[3], c01[3], c11[3];
+    unpack_r11g11b10f(t.Data[i00], c00); unpack_r11g11b10f(t.Data[i00 + 8], c10);
+    unpack_r11g11b10f(t.Data[i01], c01); unpack_r11g11b10f(t.Data[i01 + 8], c11);
+    const float fracScale = 1.0f / 256;
+    float fx = inboundX ? (float)(ixf & 255) * fracScale : 0.0f, fy = (float)(iyf & 255) * fracScale;
+    for (int k = 0; k < 3; k++) {
+        float rowA = c00[k] + (c10[k] - c00[k]) * fx, rowB = c01[k] + (c11[k] - c01[k]) * fx;
+        out[k] = rowA + (rowB - rowA) * fy;
+    }
+}
+
 // RGBA8u::UnpackSrgb — Texture.h:37-54
 inline void unpack_srgb(uint32_t packed, float out[4]) {
     uint32_t rb1 = ((packed << 8) & 0xFF00FF00u) + 0x00FF00FFu;
@@ -234,7 +278,8 @@ static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t widt
                               const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
                               const swr_light* lights, uint32_t numLights,
                               const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
-                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer);
+                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer,
+                              const swr_texture_desc* skybox = nullptr);
 
 extern "C" {
 
@@ -267,7 +312,8 @@ static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t widt
                               const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
                               const swr_light* lights, uint32_t numLights,
                               const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
-                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer) {
+                              const float* viewPos, float exposure, uint32_t yBegin, uint32_t yEnd, int debugLayer,
+                              const swr_texture_desc* skybox) {
     const float scaleU = 2.0f / (float)width, scaleV = 2.0f / (float)height;       // Rasterizer.h:226
     const float centerU = 0.5f * scaleU - 1.0f, centerV = 0.5f * scaleV - 1.0f;    // :227
     const V3 view = { viewPos[0], viewPos[1], viewPos[2] };
@@ -492,6 +538,12 @@ static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t widt
                     tileData[i] = sky[i] ? background : pack_rgba8(outColor[i][0], outColor[i][1], outColor[i][2], 1.0f);
                 continue;
             }
+            if (skybox != nullptr) {                                                 // Shading.cpp:676-679
+                for (int i = 0; i < N; i++) {
+                    if (!sky[i]) continue;
+                    sample_skybox(*skybox, { worldPos[i].x - view.x, worldPos[i].y - view.y, worldPos[i].z - view.z }, outColor[i]);
+                }
+            }
             // tonemap + pack (:680-688, Tonemap_Unreal :221-226)
             for (int i = 0; i < N; i++) {
                 float o[3];
@@ -506,6 +558,21 @@ static void resolve_rows_impl(uint32_t* color, const float* depth, uint32_t widt
 }
 
 extern "C" {
+
+// ShadingContext::Resolve with ShadingContext::SkyboxTex set (Shading.h:29, Shading.cpp:676-679): sky pixels take
+// SkyboxTex->SampleOctLevel<EnvSampler>(worldPos - ViewPos, 1); `skybox` is a Texture2D<R11G11B10f, TiledY8>.
+void orc_resolve_sky(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                     const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                     const swr_light* lights, uint32_t numLights,
+                     const float* objectToClip, const float* objectToWorld3, const float* invScreenProj,
+                     const float* viewPos, float exposure, const swr_texture_desc* skybox) {
+    resolve_rows_impl(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
+                      objectToWorld3, invScreenProj, viewPos, exposure, 0, height, kLayerNone, skybox);
+}
+
+// Probes for the known-answer tests.
+void orc_map_octahedron(const float* dir, float* uv) { map_octahedron({ dir[0], dir[1], dir[2] }, uv[0], uv[1]); }
+void orc_sample_skybox(const swr_texture_desc* tex, const float* dir, float* rgb) { sample_skybox(*tex, { dir[0], dir[1], dir[2] }, rgb); }
 
 void orc_resolve(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
                  const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,

@@ -105,7 +105,7 @@ def _texture_descs(textures):
 
 
 def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, object_to_clip, object_to_world3,
-            inv_screen_proj, view_pos, exposure: float = 1.0, world_to_clip=None, **_unused):
+            inv_screen_proj, view_pos, exposure: float = 1.0, world_to_clip=None, skybox=None, **_unused):
     """ShadingContext::Resolve on the CPU: layer 0 (surface ids) is overwritten with RGBA8 colour; with
     `world_to_clip`, point/spot lights are then drawn as markers like the tail of Resolve (Shading.cpp:690-731)."""
     assert meshlets.dtype.itemsize == 1728
@@ -113,10 +113,17 @@ def resolve(fb: Framebuffer, meshlets: np.ndarray, materials, textures, lights, 
     vp = np.ascontiguousarray(np.asarray(view_pos, dtype=np.float32))
     o2w = np.ascontiguousarray(np.asarray(object_to_world3, dtype=np.float32).reshape(9))
     lights = np.ascontiguousarray(lights)
-    lib().orc_resolve(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
-                      _p(materials) if len(materials) else None, descs, _p(lights) if len(lights) else None,
-                      C.c_uint32(len(lights)), _p(_mat(object_to_clip)), _p(o2w), _p(_mat(inv_screen_proj)), _p(vp),
-                      C.c_float(exposure))
+    if skybox is not None:      # ShadingContext::SkyboxTex (Shading.h:29): an HdrTexture2D = Texture2D<R11G11B10f>
+        sky_desc, keep_sky = _texture_descs([skybox])
+        lib().orc_resolve_sky(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
+                              _p(materials) if len(materials) else None, descs, _p(lights) if len(lights) else None,
+                              C.c_uint32(len(lights)), _p(_mat(object_to_clip)), _p(o2w), _p(_mat(inv_screen_proj)), _p(vp),
+                              C.c_float(exposure), sky_desc)
+    else:
+        lib().orc_resolve(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
+                          _p(materials) if len(materials) else None, descs, _p(lights) if len(lights) else None,
+                          C.c_uint32(len(lights)), _p(_mat(object_to_clip)), _p(o2w), _p(_mat(inv_screen_proj)), _p(vp),
+                          C.c_float(exposure))
     if world_to_clip is not None and len(lights):
         draw_light_markers(fb, lights, world_to_clip)
 
@@ -134,6 +141,23 @@ def resolve_debug(fb: Framebuffer, meshlets: np.ndarray, materials, textures, la
     lib().orc_resolve_debug(_p(fb.data[0]), _p(fb.data[1]), C.c_uint32(fb.width), C.c_uint32(fb.height), _p(meshlets),
                             _p(materials) if len(materials) else None, descs, _p(_mat(object_to_clip)), _p(o2w),
                             _p(_mat(inv_screen_proj)), C.c_int(layer))
+
+
+def map_octahedron(direction) -> np.ndarray:
+    """texutil::MapOctahedron (Texture.h:282-288) of one direction."""
+    d = np.ascontiguousarray(np.asarray(direction, dtype=np.float32))
+    uv = np.zeros(2, dtype=np.float32)
+    lib().orc_map_octahedron(_p(d), _p(uv))
+    return uv
+
+
+def sample_skybox(tex, direction) -> np.ndarray:
+    """HdrTexture2D::SampleOctLevel<EnvSampler>(dir, 1) (Texture.h:467-480) of one direction."""
+    descs, keep = _texture_descs([tex])
+    d = np.ascontiguousarray(np.asarray(direction, dtype=np.float32))
+    rgb = np.zeros(3, dtype=np.float32)
+    lib().orc_sample_skybox(descs, _p(d), _p(rgb))
+    return rgb
 
 
 def draw_light_markers(fb: Framebuffer, lights, world_to_clip) -> None:
