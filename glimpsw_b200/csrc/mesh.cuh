@@ -88,7 +88,9 @@ __device__ __forceinline__ void raster_inline(const TriRecord& t, const BBox& r,
 }
 
 template <bool kBinned>
-__global__ void __launch_bounds__(kMeshWarps * 32, 4)      // 64 registers: 4 blocks = 32 warps per SM
+// Persistent grid of 1..4 blocks per SM (swrb_device_set_mesh_occupancy): 4 = the whole register file for a lone frame,
+// 1 leaves room for other render contexts' resolve blocks, whose issue-bound warps fill what these latency-bound ones leave idle.
+__global__ void __launch_bounds__(kMeshWarps * 32, 4)      // 64 registers: up to 4 blocks = 32 warps per SM
 k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
              const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
              unsigned long long* __restrict__ keys,
