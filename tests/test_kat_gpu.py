@@ -142,3 +142,57 @@ def test_framebuffer_ops_and_errors(rast_factory):
             rast.create_framebuffer(*bad)
     with pytest.raises(api.SwrbError):
         fb.clear(0, -1.0)
+
+
+def _ragged_meshlets(seed, count, spread):
+    """Random meshlets with every vertex / triangle count from empty to full (0..128 triangles, 3..64 vertices), random
+    windings, tiny to guard-band-sized triangles, some behind the camera plane."""
+    from glimpsw_b200.layout import MESHLET_DTYPE
+    rng = np.random.default_rng(seed)
+    m = np.zeros(count, dtype=MESHLET_DTYPE)
+    m["MaterialId"] = 0xFFFFFFFF
+    m["AlphaCutoff"] = 255
+    for i in range(count):
+        nv = int(rng.integers(3, 65))
+        nt = int(rng.choice([0, 1, 15, 16, 17, 31, 32, 33, 97, 127, 128, int(rng.integers(0, 129))]))
+        centre = rng.uniform(-0.9, 0.9, 3) * (1.0, 1.0, 0.0) + (0.0, 0.0, rng.uniform(0.05, 0.9))
+        size = float(rng.choice([0.002, 0.01, 0.05, 0.3, spread]))
+        m["Positions"][i, :, :nv] = (centre[:, None] + rng.uniform(-size, size, (3, nv))).astype(np.float32)
+        m["Indices"][i, :, :nt] = rng.integers(0, nv, (3, nt))
+        m["NumVertices"][i], m["NumTriangles"][i] = nv, nt
+        m["BoundCenter"][i] = centre
+        m["BoundRadius"][i] = size * 2
+    return m
+
+
+@MODES
+@pytest.mark.parametrize("seed,spread", [(1, 0.6), (2, 3.0), (3, 40.0)])
+def test_ragged_and_empty_meshlets(orc, rast_factory, binning, seed, spread):
+    """Edge cases of the input format: empty meshlets, counts that are not multiples of the 16-wide packet or the 32-wide
+    round, degenerate / repeated indices, triangles from sub-pixel to far beyond the guard band, w <= 0 vertices."""
+    from glimpsw_b200 import camera as cam
+    meshlets = _ragged_meshlets(seed, 97, spread)
+    w, h = 1000, 564
+    # a perspective-ish matrix: w = z, so vertices with z <= 0 are behind the camera plane
+    m = np.zeros((4, 4), dtype=np.float32)
+    m[0, 0], m[1, 1], m[2, 2], m[2, 3], m[3, 2] = 1.0, 1.0, 0.0, 1.0, 0.01
+    ofb = orc.Framebuffer(w, h)
+    ofb.clear(0xFF000000, 0.0)
+    clipping = not binning
+    oc = orc.draw_meshlets(ofb, meshlets, 0, len(meshlets), m, binned=binning, clipping=clipping)
+    rast = rast_factory(enable_binning=binning, enable_clipping=clipping)
+    gscene = rast.upload_scene(meshlets)
+    fb = rast.create_framebuffer(w, h)
+    fb.clear(0xFF000000, 0.0)
+    rast.reset_counters()
+    rast.draw_meshlets(fb, gscene, 0, len(meshlets), m)
+    assert_visbuffer_equal(ofb, fb, f"ragged seed {seed}")
+    c = rast.counters()
+    assert [c["TrianglesProcessed"], c["TrianglesRasterized"], c["TrianglesClipped"]] == [int(oc[0]), int(oc[1]), int(oc[2])]
+    assert int(oc[0]) == int(meshlets["NumTriangles"].astype(np.int64).sum())
+    # a draw of zero meshlets and an all-zero cull bitmap leave the framebuffer alone
+    before = (fb.download_tiled(0), fb.download_tiled(1))
+    rast.draw_batch(fb, gscene, [])
+    rast.draw_meshlets(fb, gscene, 5, 0, m)
+    rast.draw_meshlets(fb, gscene, 0, len(meshlets), m, cull_bitmap=np.zeros((len(meshlets) + 15) // 16, dtype=np.uint16))
+    assert np.array_equal(before[0], fb.download_tiled(0)) and np.array_equal(before[1], fb.download_tiled(1))
