@@ -138,6 +138,18 @@ def test_import_reference_sponza_lowpoly(orc):
     assert int(counters[0]) == 63084 and (ofb.data[1, :n].view(np.float32) > 0).mean() > 0.9      # RasterBench.cpp:68 looks down the atrium
 
 
+@pytest.mark.skipif(not os.path.exists(SPONZA), reason="reference assets are not on this machine")
+def test_reference_sponza_lowpoly_matches_committed_golden():
+    """tests/golden/sponza_lowpoly_hashes.json (make_golden_sponza.py): importer + oracle on the reference's own asset,
+    binned and unbinned-with-clipping (the mode RasterBench.cpp:77 uses), from the RasterBench camera."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_sponza
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sponza_lowpoly_hashes.json")))
+    assert make_golden_sponza.digest() == want
+    assert want["unbinned_clipped"]["counters"][1] >= want["binned"]["counters"][1]      # clipped pieces are rasterized too
+
+
 @pytest.mark.gpu
 def test_imported_scene_parity(tmp_path, orc, rast_factory):
     path, *_ = _write_test_gltf(tmp_path)
