@@ -20,6 +20,7 @@
 // restatement used as the timed CPU baseline, and must equal this file bit for bit.
 
 #include <cmath>
+#include <immintrin.h>
 #include <cstdint>
 #include <cstring>
 #include <cfenv>
@@ -47,9 +48,21 @@ inline Vec4 mul_mat4_pos(const float* m, float x, float y, float z) {
     r.w = std::fmaf(x, m[0 * 4 + 3], std::fmaf(y, m[1 * 4 + 3], std::fmaf(z, m[2 * 4 + 3], 1.0f * m[3 * 4 + 3])));
     return r;
 }
+// ---- sensitivity switch: what the upstream BINARY most likely computes for `1.0f / x` ----------------
+// The reference is built with -ffast-math (src/SwRast/CMakeLists.txt:6); for 512-bit vector divisions clang then emits
+// vrcp14ps plus one Newton-Raphson step instead of vdivps. Mode 1 emulates that (rcp14 estimate e, e + e * (1 - x * e)
+// with FMAs, numerator multiplied afterwards) so tools/rcp14_sensitivity.py can measure how far such a binary would be
+// from the canonical IEEE arithmetic (mode 0, the default, the only mode parity is defined against).
+int g_rcpMode = 0;
+__attribute__((target("avx512f"))) inline float rcp14_nr(float x) {
+    float e = _mm_cvtss_f32(_mm_rcp14_ss(_mm_setzero_ps(), _mm_set_ss(x)));
+    return std::fmaf(std::fmaf(-x, e, 1.0f), e, e);
+}
+inline float oracle_rcp(float x) { return g_rcpMode ? rcp14_nr(x) : 1.0f / x; }
+
 // simd::perspective_div — SIMD.h:473-476
 inline Vec4 perspective_div(Vec4 v) {
-    float rw = 1.0f / v.w;
+    float rw = oracle_rcp(v.w);
     return { v.x * rw, v.y * rw, v.z * rw, rw };
 }
 
@@ -144,7 +157,7 @@ inline void edge_setup(const TriSetup& t, int halfW, int halfH, TriEdges& e) {
     e.Edge1 = compute_edge(e.A20, sampleX - x2, e.B20, sampleY - y2);
     e.Edge2 = compute_edge(e.A01, sampleX - x0, e.B01, sampleY - y0);
 
-    float rcpArea = 16.0f / (float)det;                                       // :320
+    float rcpArea = g_rcpMode ? 16.0f * rcp14_nr((float)det) : 16.0f / (float)det;   // :320
     e.Z0 = t.Z0;
     e.Z10 = (t.Z1 - t.Z0) * rcpArea;
     e.Z20 = (t.Z2 - t.Z0) * rcpArea;
@@ -581,6 +594,14 @@ uint32_t orc_cull_meshlets(uint16_t* bitmap, const swr_meshlet* meshlets, uint32
         bitmap[offset / 16] = bits;
     }
     return visibleCount;
+}
+
+// 0 = canonical IEEE division (default); 1 = vrcp14ps + one Newton-Raphson step (sensitivity study only).
+// Returns -1 (mode unchanged) when the host CPU has no AVX-512F.
+int orc_set_reciprocal_mode(int mode) {
+    if (mode != 0 && !__builtin_cpu_supports("avx512f")) return -1;
+    g_rcpMode = mode != 0;
+    return 0;
 }
 
 const char* orc_build_info() {

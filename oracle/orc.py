@@ -275,3 +275,10 @@ def probe_triangle(verts, width: int, height: int, cull_mode: int = 1, guardband
     keep = lib().orc_probe_triangle(_p(v), width, height, cull_mode, 1 if guardband else 0, C.byref(cc),
                                     _p(pos), _p(bbox), _p(edges), _p(zw))
     return dict(keep=int(keep), cc=cc.value, pos=pos, bbox=bbox, edges=edges, zw=zw)
+
+
+def set_reciprocal_mode(mode: int) -> bool:
+    """0 = canonical IEEE division (default, what parity is defined against); 1 = vrcp14ps + one Newton-Raphson step, the
+    code clang most likely emits for the reference's -ffast-math vector divisions. Sensitivity studies
+    only (tools/rcp14_sensitivity.py). Returns False when the host has no AVX-512F (mode unchanged)."""
+    return lib().orc_set_reciprocal_mode(C.c_int(mode)) == 0

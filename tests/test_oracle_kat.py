@@ -6,9 +6,12 @@ bounding box with its carry quirk (:331-351), the guard-band cl
 (:353-397), the reverse-Z strict depth test (Shading.cpp:311-313) and the one-worker draw order — not
 from the oracle's own output. tests/golden/ additionally pins whole-frame hashes (regression only).
 """
+import os
+
 import numpy as np
 import pytest
 
+from helpers import oracle_render
 from glimpsw_b200.layout import MESHLET_DTYPE, MATERIAL_DTYPE, NO_MATERIAL, detile
 
 IDENT = np.eye(4, dtype=np.float32)
@@ -213,3 +216,26 @@ def test_cull_meshlets_planes_and_bitmap(orc):
         assert np.array_equal(bits[sure].astype(bool), ok[sure])
         total_visible += n
     assert total_visible > 0
+
+
+def test_rcp14_newton_sensitivity_is_confined_to_depth_ulps(orc):
+    """an upstream -ffast-math binary most likely divides with vrcp14ps + one Newton step. Rendering with
+    that arithmetic (oracle mode 1) instead of IEEE division (mode 0, the canonical one) must leave coverage, surface
+    ids and counters alone on the reduced BASELINE scenes and move depth words by a few ulp on well under 1 % of pixels —
+    the size of the gap to the upstream binary that no port can close (tools/rcp14_sensitivity.py prints the full table)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    if not orc.set_reciprocal_mode(1):
+        pytest.skip("host CPU has no AVX-512F (vrcp14ss)")
+    orc.set_reciprocal_mode(0)
+    import rcp14_sensitivity
+    from glimpsw_b200 import scenes
+    for scene, cull in ((scenes.grid_scene(40, 32, 1280, 720, seed=3), False), (scenes.torus_knot_scene(120, 48, 960, 540, tex_size=64), False)):
+        r = rcp14_sensitivity.compare(scene, cull)
+        assert r["ids_differ"] == 0 and r["coverage_differs"] == 0 and r["counters_ieee"] == r["counters_rcp14_nr"]
+        assert 0 < r["depth_words_differ"] < 0.01 * r["covered"] and r["max_depth_ulp"] <= 4
+    # the switch is off again: the canonical mode is what every other test runs in
+    fb, _ = oracle_render(orc, scenes.grid_scene(20, 16, 640, 360, seed=3, flip_fraction=0.2))
+    import hashlib, json
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "visbuffer_hashes.json")))["c2_small_640x360"]
+    assert hashlib.sha256(fb.data[1, :640 * 360].tobytes()).hexdigest() == golden["depth_sha256"]
