@@ -409,6 +409,10 @@ def run_ours(args):
                              f"({F * copies * scene.meshlets.nbytes / 1e6:.0f} MB > 126 MB); latency mode evicts L2 (256 MB write + 256 MB read) before every frame",
                        "timing": "one CUDA-event pair around the K frames on the launching streams (all contexts joined), max over ranks"},
             "frames_per_s": round(world / (ms_per_step * 1e-3), 1),
+            # `value` counts submitted triangles; the same rate for the triangles that survive meshlet culling
+            # (Rasterizer.cpp:545) and for those that are rasterized (:579)
+            "processed_Mtri_s": round(counters["TrianglesProcessed"] * world / (ms_per_step * 1e-3) / 1e6, 2),
+            "rasterized_Mtri_s": round(counters["TrianglesRasterized"] * world / (ms_per_step * 1e-3) / 1e6, 2),
             "latency_ms_per_frame": round(float(np.median(lat_ms)), 5),
             "latency_ms_min_max": [round(float(np.min(lat_ms)), 5), round(float(np.max(lat_ms)), 5)],
             "wall_ms_per_step": round(t_wall / args.steps * 1e3, 4),

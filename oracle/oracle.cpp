@@ -13,7 +13,8 @@
 // exactly where the source writes simd::fma / simd::mul / simd::dot, separately rounded
 // * + - elsewhere, correctly rounded '/', float->int by RNE (vcvtps2dq), wrapping int32.
 // (The upstream build uses -ffast-math, under which clang may turn 1.0f/x into
-// vrcp14ps+Newton; that is not reproducible off x86 — SURVEY.md App. B.1.)
+// vrcp14ps+Newton; that is not reproducible off x86 — SURVEY.md App. B.1. orc_set_reciprocal_mode(1)
+// emulates it on AVX-512 hosts, for the sensitivity study of tools/rcp14_sensitivity.py only.)
 //
 // Build: g++ -O2 -march=x86-64-v3 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
 // Scalar on purpose: this file is the spec. oracle/baseline_mt.cpp is the threaded
