@@ -35,6 +35,11 @@ extern "C" void orc_resolve_rows(uint32_t* color, const float* depth, uint32_t w
                                  const swr_light* lights, uint32_t numLights, const float* objectToClip,
                                  const float* objectToWorld3, const float* invScreenProj, const float* viewPos, float exposure,
                                  uint32_t yBegin, uint32_t yEnd);
+extern "C" void orc_resolve_rows_avx512(uint32_t* color, const float* depth, uint32_t width, uint32_t height,
+                                 const swr_meshlet* meshlets, const swr_material* materials, const swr_texture_desc* textures,
+                                 const swr_light* lights, uint32_t numLights, const float* objectToClip,
+                                 const float* objectToWorld3, const float* invScreenProj, const float* viewPos, float exposure,
+                                 uint32_t yBegin, uint32_t yEnd);
 
 namespace {
 
@@ -324,8 +329,14 @@ void orc_mt_resolve(void* p, uint32_t* color, const float* depth, uint32_t width
         for (;;) {
             uint32_t y = nextRow.fetch_add(32, std::memory_order_relaxed);
             if (y >= height) break;
-            orc_resolve_rows(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
-                             objectToWorld3, invScreenProj, viewPos, exposure, y, std::min(y + 32, height));
+            // 16 pixels per step like the reference (one 4x4 fragment = one AVX-512 vector) where the CPU has AVX-512;
+            // the scalar spec otherwise. Both produce the same bits (tests/test_baseline_cpu.py).
+            if (pool.avx512)
+                orc_resolve_rows_avx512(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
+                                        objectToWorld3, invScreenProj, viewPos, exposure, y, std::min(y + 32, height));
+            else
+                orc_resolve_rows(color, depth, width, height, meshlets, materials, textures, lights, numLights, objectToClip,
+                                 objectToWorld3, invScreenProj, viewPos, exposure, y, std::min(y + 32, height));
         }
     });
 }
