@@ -255,7 +255,8 @@ def run_ours(args):
 
     # ---- timed region (throughput): exactly K frames, F in flight, inputs larger than L2
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:               # one nvidia-smi poller per job, on the rank that prints: NVML queries from 8 pollers perturb the
+        sampler.start()         # very launches they are meant to watch
     launches0 = sum(c.rast.launch_count() for c in ctxs)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
