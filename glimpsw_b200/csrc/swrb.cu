@@ -229,6 +229,22 @@ static int check_overflow(swrb_device* d) {
 extern "C" {
 
 static int fb_materialize_for_read(swrb_fb* fb, uint32_t layer);
+void swrb_device_destroy(swrb_device* d);
+void swrb_scene_destroy(swrb_scene* s);
+void swrb_fb_destroy(swrb_fb* fb);
+void swrb_hiz_destroy(swrb_hiz* z);
+}
+
+// A half-built object is torn down by its own destroy function when a create call fails part-way
+// (every CU(...) inside returns early): the destroy functions tolerate null members.
+template <class T, void (*Destroy)(T*)>
+struct CreateGuard {
+    T* p;
+    ~CreateGuard() { if (p) Destroy(p); }
+    T* release() { T* r = p; p = nullptr; return r; }
+};
+
+extern "C" {
 
 const char* swrb_last_error(void) { return g_lastError.c_str(); }
 const char* swrb_version(void) { return "swrb 0.1 (sm_100a)"; }
@@ -241,7 +257,8 @@ int swrb_device_create(int cuda_device, swrb_device** out) {
         return fail(SWRB_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (cuda_device < 0 || cuda_device >= n) return fail(SWRB_E_INVALID, "cuda_device %d out of range (%d devices)", cuda_device, n);
     CU(cudaSetDevice(cuda_device));
-    swrb_device* d = new swrb_device();
+    CreateGuard<swrb_device, swrb_device_destroy> guard{ new swrb_device() };
+    swrb_device* d = guard.p;
     d->cudaDevice = cuda_device;
     CU(cudaDeviceGetAttribute(&d->numSMs, cudaDevAttrMultiProcessorCount, cuda_device));
     CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
@@ -252,7 +269,7 @@ int swrb_device_create(int cuda_device, swrb_device** out) {
     CU(cudaEventCreate(&d->timerBegin));
     CU(cudaEventCreate(&d->timerEnd));
     for (int i = 0; i < swrb_device::kStagingSlots; i++) CU(cudaEventCreateWithFlags(&d->drawStagingDone[i], cudaEventDisableTiming));
-    *out = d;
+    *out = guard.release();
     return SWRB_OK;
 }
 
@@ -338,7 +355,8 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
     if (num_meshlets && !meshlets) return fail(SWRB_E_INVALID, "meshlets is null");
     CU(cudaSetDevice(d->cudaDevice));
-    swrb_scene* s = new swrb_scene();
+    CreateGuard<swrb_scene, swrb_scene_destroy> guard{ new swrb_scene() };
+    swrb_scene* s = guard.p;
     s->dev = d;
     s->numMeshlets = num_meshlets;
     s->attrDirtyLo = 0; s->attrDirtyHi = num_meshlets;
@@ -381,7 +399,7 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
         s->lightsHost.assign(lights, lights + num_lights);
     }
     CU(cudaStreamSynchronize(d->stream));   // host inputs are only borrowed for the duration of the call
-    *out = s;
+    *out = guard.release();
     return SWRB_OK;
 }
 
@@ -436,12 +454,13 @@ int swrb_fb_create(swrb_device* d, uint32_t width, uint32_t height, uint32_t num
     if (width > SWR_MAX_RENDER_SIZE || height > SWR_MAX_RENDER_SIZE) return fail(SWRB_E_INVALID, "framebuffer size %ux%u exceeds MaxRenderSize %d (Rasterizer.h:203)", width, height, SWR_MAX_RENDER_SIZE);
     if (num_layers < 2) return fail(SWRB_E_INVALID, "need at least 2 layers (colour/id + depth)");
     CU(cudaSetDevice(d->cudaDevice));
-    swrb_fb* fb = new swrb_fb();
+    CreateGuard<swrb_fb, swrb_fb_destroy> guard{ new swrb_fb() };
+    swrb_fb* fb = guard.p;
     fb->dev = d; fb->width = width; fb->height = height; fb->layers = num_layers;
     fb->layerStride = (width * height + 63u) & ~63u;                      // Rasterizer.h:69
     CU(cudaMalloc(&fb->data, (size_t)fb->layerStride * num_layers * 4 + 256));
     CU(cudaMemsetAsync(fb->data, 0, (size_t)fb->layerStride * num_layers * 4, d->stream));
-    *out = fb;
+    *out = guard.release();
     return SWRB_OK;
 }
 
@@ -729,7 +748,8 @@ int swrb_hiz_create(swrb_device* d, uint32_t fb_width, uint32_t fb_height, swrb_
     auto bit_length = [](uint32_t v) { uint32_t n = 0; while (v) { n++; v >>= 1; } return n; };
     // Main.cpp:54-56: halfW = 1 << (32 - lzcnt((width - 1) / 2)); CreateTexture2D<R32f>(halfW, halfH, 16)
     uint32_t w = 1u << bit_length((fb_width - 1) / 2), h = 1u << bit_length((fb_height - 1) / 2);
-    swrb_hiz* z = new swrb_hiz();
+    CreateGuard<swrb_hiz, swrb_hiz_destroy> guard{ new swrb_hiz() };
+    swrb_hiz* z = guard.p;
     z->dev = d;
     z->desc.width = w; z->desc.height = h;
     z->desc.rowShift = 0;
@@ -745,7 +765,7 @@ int swrb_hiz_create(swrb_device* d, uint32_t fb_width, uint32_t fb_height, swrb_
     z->layerStride = stride;
     CU(cudaMalloc(&z->desc.data, (size_t)stride * 4 + 256));
     CU(cudaMemsetAsync(z->desc.data, 0, (size_t)stride * 4, d->stream));
-    *out = z;
+    *out = guard.release();
     return SWRB_OK;
 }
 
