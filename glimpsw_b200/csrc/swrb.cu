@@ -426,9 +426,12 @@ int swrb_scene_set_skybox(swrb_scene* s, const swr_texture_desc* hdr) {
     if (!hdr->Data || hdr->Width < 8 || hdr->Height < 8 || (hdr->Width & (hdr->Width - 1)) || (hdr->Height & (hdr->Height - 1)) || hdr->MipLevels < 1 || hdr->MipLevels > 16)
         return fail(SWRB_E_INVALID, "skybox must be a power-of-two Texture2D<R11G11B10f> of at least 8x8 texels with 1..16 mip levels");
     const size_t texels = (size_t)hdr->LayerStride * std::max(1u, hdr->NumLayers);
-    CU(cudaMalloc(&s->skyData, texels * 4 + 256));
-    CU(cudaMemcpyAsync(s->skyData, hdr->Data, texels * 4, cudaMemcpyHostToDevice, d->stream));
-    CU(cudaStreamSynchronize(d->stream));            // the host texels are only borrowed for the call
+    uint32_t* data = nullptr;
+    CU(cudaMalloc(&data, texels * 4 + 256));
+    cudaError_t e = cudaMemcpyAsync(data, hdr->Data, texels * 4, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);      // the host texels are only borrowed for the call
+    if (e != cudaSuccess) { cudaFree(data); return fail(SWRB_E_CUDA, "skybox upload: %s", cudaGetErrorString(e)); }
+    s->skyData = data;                               // only a completely uploaded skybox becomes visible to swrb_resolve
     ResolveTexture& r = s->sky;
     r.data = s->skyData;
     r.width = hdr->Width; r.height = hdr->Height; r.mipLevels = hdr->MipLevels; r.numLayers = hdr->NumLayers;
