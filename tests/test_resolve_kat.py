@@ -210,3 +210,45 @@ def test_gpu_directional_light_matches_float64_brdf(orc, rast_factory, metal, ro
     got = fb.get_pixels(0)
     d = np.abs(got.view(np.uint8).astype(np.int32) - want.view(np.uint8).astype(np.int32))
     assert d.max() <= 2
+
+
+# ---- the alpha-tested fragment program FS_EncodeSurfaceId<true> (Shading.cpp:309-331) --------------------------------
+def _alpha_scene(size):
+    tex = tx.create_texture(size, size, 1, 1)
+    y, x = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    alpha = np.where(((x // 2) + (y // 3)) % 2 == 0, 255, 0)                      # 2 x 3 texel blocks, on / off
+    tx.set_pixels(tex, (0x00406080 | (alpha.astype(np.uint32) << 24)), 0)
+    meshlets, m, mats, textures = quad_scene(size, tex=tex)
+    mats["AlphaCutoff"] = 128
+    meshlets["AlphaCutoff"] = 128                                                  # Scene.cpp:246: copied from the material
+    return meshlets, m, mats, textures, alpha
+
+
+def test_alpha_test_coverage_equals_the_texture_alpha_mask(orc):
+    """1:1 mapping: pixel (x, y) samples texel (x, y) (bilinear with a 1/256 weight of the right / lower neighbour, which
+    moves alpha by at most 1 — Texture.h:506-575, SIMD.h:448-450), so a pixel is written iff its texel's alpha >= cutoff."""
+    size = 64
+    meshlets, m, mats, textures, alpha = _alpha_scene(size)
+    fb = orc.Framebuffer(size, size)
+    fb.clear(0xFFFFFFFF, 0.0)
+    c = orc.draw_meshlets(fb, meshlets, 0, len(meshlets), m, materials=mats, textures=textures)
+    assert int(c[1]) == 2
+    depth = detile(fb.data[1, :size * size], size, size).view(np.float32)
+    ids = detile(fb.data[0, :size * size], size, size)
+    assert np.array_equal(depth > 0, alpha == 255)
+    assert np.all(depth[alpha == 255] == 0.5) and np.all(ids[alpha == 0] == 0xFFFFFFFF)
+
+
+@pytest.mark.gpu
+def test_gpu_alpha_test_coverage_equals_the_texture_alpha_mask(rast_factory):
+    size = 64
+    meshlets, m, mats, textures, alpha = _alpha_scene(size)
+    for binning in (True, False):
+        rast = rast_factory(enable_binning=binning)
+        gscene = rast.upload_scene(meshlets, mats, textures)
+        fb = rast.create_framebuffer(size, size)
+        fb.clear(0xFFFFFFFF, 0.0)
+        rast.draw_meshlets(fb, gscene, 0, len(meshlets), m)
+        depth = fb.get_pixels(1).view(np.float32)
+        assert np.array_equal(depth > 0, alpha == 255) and np.all(depth[alpha == 255] == 0.5)
+        assert np.all(fb.get_pixels(0)[alpha == 0] == 0xFFFFFFFF)
