@@ -196,3 +196,31 @@ def test_ragged_and_empty_meshlets(orc, rast_factory, binning, seed, spread):
     rast.draw_meshlets(fb, gscene, 5, 0, m)
     rast.draw_meshlets(fb, gscene, 0, len(meshlets), m, cull_bitmap=np.zeros((len(meshlets) + 15) // 16, dtype=np.uint16))
     assert np.array_equal(before[0], fb.download_tiled(0)) and np.array_equal(before[1], fb.download_tiled(1))
+
+
+def test_ragged_fuzz_many_seeds(orc, rast_factory):
+    """24 more seeds of the ragged generator over four framebuffer sizes (incl. the 2896^2 limit) and four triangle-size
+    regimes, binned and unbinned + clipping: vis-buffer and counters bit-exact every time."""
+    m = np.zeros((4, 4), dtype=np.float32)
+    m[0, 0], m[1, 1], m[2, 3], m[3, 2] = 1.0, 1.0, 1.0, 0.01
+    rasts = {True: rast_factory(enable_binning=True, enable_clipping=False), False: rast_factory(enable_binning=False, enable_clipping=True)}
+    for seed in range(100, 124):
+        spread = [0.3, 1.5, 8.0, 60.0][seed % 4]
+        w, h = [(1000, 564), (640, 360), (1280, 720), (64, 64)][(seed // 4) % 4]
+        if seed == 108:
+            w, h = 2896, 2896
+        meshlets = _ragged_meshlets(seed, 61, spread)
+        for binning, rast in rasts.items():
+            ofb = orc.Framebuffer(w, h)
+            ofb.clear(0xFF000000, 0.0)
+            oc = orc.draw_meshlets(ofb, meshlets, 0, len(meshlets), m, binned=binning, clipping=not binning)
+            gscene = rast.upload_scene(meshlets)
+            fb = rast.create_framebuffer(w, h)
+            fb.clear(0xFF000000, 0.0)
+            rast.reset_counters()
+            rast.draw_meshlets(fb, gscene, 0, len(meshlets), m)
+            assert_visbuffer_equal(ofb, fb, f"fuzz seed {seed} {w}x{h} binning={binning}")
+            c = rast.counters()
+            assert [c["TrianglesProcessed"], c["TrianglesRasterized"], c["TrianglesClipped"]] == [int(oc[0]), int(oc[1]), int(oc[2])], seed
+            fb.destroy()
+            gscene.destroy()
