@@ -7,8 +7,9 @@ handedness bits), nodes walked depth-first with `GlobalTransform = parent * loca
 
 What differs from the reference, by necessity (none of its third-party importers exist in this image):
   * cgltf -> the JSON + buffer parsing below (`.gltf` with external / data-URI buffers, and `.glb`);
-  * meshoptimizer's `meshopt_buildMeshlets` -> the greedy scan of `scenes.meshletize` (different meshlet boundaries
-    = different surface ids, same geometry) and a centroid bounding sphere instead of `meshopt_computeMeshletBounds`;
+  * meshoptimizer's `meshopt_buildMeshlets` -> `adjacency_order` (grow each meshlet over shared vertices, cheapest
+    triangle first) + the cutting scan of `scenes.meshletize` (different meshlet boundaries = different surface ids, same
+    geometry) and a bounding-box sphere instead of `meshopt_computeMeshletBounds`;
   * stb_image -> Pillow for the texture files.
 Everything downstream (the meshlet bytes, materials, texture layout, uniforms) is the reference's format, so an imported
 scene goes through `api.Rasterizer.upload_scene` / the oracle like the procedural ones.
@@ -171,6 +172,79 @@ def _node_local(n: dict) -> np.ndarray:
     return t @ r @ s
 
 
+def adjacency_order(tris: np.ndarray, max_verts: int = 64, max_tris: int = 128) -> np.ndarray:
+    """Triangle order for the meshletizer, grown by adjacency like meshopt_buildMeshlets (Scene.cpp:199-237) grows its
+    meshlets: the next triangle is one that shares vertices with the meshlet under construction, preferring those that add no
+    new vertex, then one, then two; when the meshlet is full the next one is seeded from a neighbour of the old one.
+    `scenes.meshletize` (a linear scan that cuts whenever a limit is hit) then finds the same cuts, so an index buffer in
+    arbitrary order still yields well-filled meshlets. Returns a permutation of range(len(tris))."""
+    tris = np.asarray(tris, dtype=np.int64)
+    n = len(tris)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    T = tris.tolist()
+    adj: dict = {}
+    for t, (a, b, c) in enumerate(T):
+        for v in (a, b, c):
+            adj.setdefault(v, []).append(t)
+    done = [False] * n
+    order = []
+    in_meshlet: set = set()
+    missing: dict = {}                    # candidate triangle -> number of its vertices not yet in the meshlet
+    buckets = (set(), set(), set(), set())
+    num_tris = 0
+    next_unseen = 0
+
+    def add_vertex(v):
+        in_meshlet.add(v)
+        for t in adj[v]:
+            if done[t]:
+                continue
+            k = missing.get(t)
+            if k is None:
+                k = len({x for x in T[t] if x not in in_meshlet})
+            else:
+                buckets[k].discard(t)
+                k -= 1
+            missing[t] = k
+            buckets[k].add(t)
+
+    def reset(seed_candidates):
+        nonlocal num_tris
+        in_meshlet.clear()
+        missing.clear()
+        for bkt in buckets:
+            bkt.clear()
+        num_tris = 0
+        return next((t for t in seed_candidates if not done[t]), None)
+
+    seed = None
+    while len(order) < n:
+        t = None
+        room = max_verts - len(in_meshlet)
+        if num_tris < max_tris:
+            for k in range(0, min(room, 3) + 1):
+                if buckets[k]:
+                    t = buckets[k].pop()
+                    break
+        if t is None:                                   # meshlet full (or nothing adjacent left): start the next one nearby
+            leftovers = [x for bkt in buckets for x in bkt]
+            seed = reset(leftovers)
+            if seed is None:
+                while done[next_unseen]:
+                    next_unseen += 1
+                seed = next_unseen
+            t = seed
+        missing.pop(t, None)
+        done[t] = True
+        order.append(t)
+        num_tris += 1
+        for v in dict.fromkeys(T[t]):
+            if v not in in_meshlet:
+                add_vertex(v)
+    return np.asarray(order, dtype=np.int64)
+
+
 def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Camera | None = None,
                 flip_winding: bool = False) -> SceneData:
     """Scene::ImportGltf. Returns a SceneData (meshlets, one DrawNode per glTF node with a mesh, materials, textures,
@@ -204,6 +278,7 @@ def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Ca
             if nrm is not None and tan is None:
                 tan = np.zeros((len(pos), 4), dtype=f32)                        # glm::vec4 tangent = 0 (Scene.cpp:258)
             mat_id = prim.get("material", None)
+            tris = tris[adjacency_order(tris)]                                   # meshopt_buildMeshlets stand-in (Scene.cpp:218-221)
             m = meshletize(pos, tris, uv=uv, normals=nrm, tangents=tan,
                            material_id=NO_MATERIAL if mat_id is None else mat_id,
                            alpha_cutoff=255 if mat_id is None else int(materials[mat_id]["AlphaCutoff"]))

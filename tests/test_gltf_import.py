@@ -118,6 +118,36 @@ def test_import_matches_source_arrays(tmp_path, glb):
     assert np.isclose(l["InvRadiusSq"], 1 / 81.0) and np.isclose(l["SpotScale"], 1.0 / (np.cos(0.2) - np.cos(0.6)), rtol=1e-5)
 
 
+def test_adjacency_order_fills_meshlets_from_a_shuffled_index_buffer():
+    """The meshopt_buildMeshlets stand-in: a 64 x 64-vertex grid whose 7,938 triangles arrive in random order. Cutting
+    that stream linearly gives ~20 triangles per 64-vertex meshlet; grown by adjacency it must give > 80, keep every
+    triangle exactly once and respect both limits."""
+    n = 64
+    idx = np.arange(n * n).reshape(n, n)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    tris = np.concatenate([np.stack([a, c, b], 1), np.stack([b, c, d], 1)])
+    rng = np.random.default_rng(5)
+    tris = tris[rng.permutation(len(tris))]
+    y, x = np.meshgrid(np.arange(n, dtype=np.float32), np.arange(n, dtype=np.float32), indexing="ij")
+    pos = np.stack([x.ravel(), y.ravel(), np.zeros(n * n, dtype=np.float32)], 1)
+    order = gltf.adjacency_order(tris)
+    assert sorted(order.tolist()) == list(range(len(tris)))
+    naive, grown = scenes.meshletize(pos, tris), scenes.meshletize(pos, tris[order])
+    for m in (naive, grown):
+        assert int(m["NumTriangles"].astype(np.int64).sum()) == len(tris)
+        assert (m["NumVertices"] <= 64).all() and (m["NumTriangles"] <= 128).all()
+    assert len(tris) / len(naive) < 30 and len(tris) / len(grown) > 80
+    # same triangles (as sets of positions), only regrouped
+    def tri_set(ms):
+        out = set()
+        for ml in ms:
+            for k in range(int(ml["NumTriangles"])):
+                p = np.stack([ml["Positions"][:, ml["Indices"][c, k]] for c in range(3)])
+                out.add(tuple(np.sort(p.view(np.uint32), axis=0).reshape(-1).tolist()))
+        return out
+    assert tri_set(naive) == tri_set(grown)
+
+
 def test_combine_normal_mr_and_emissive_mask():
     n = np.array([[[127, 127, 254, 9], [254, 127, 127, 9]]], dtype=np.uint8)          # +Z and +X normals
     mr = np.array([[[1, 2, 3, 4], [5, 6, 7, 8]]], dtype=np.uint8)
