@@ -79,7 +79,7 @@ class PeerComposites:
         self.buf = symm_mem.empty((slots, world, height, width), dtype=torch.int32, device="cuda")
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.root = self.hdl.get_buffer(0, self.buf.shape, self.buf.dtype)   # rank 0's buffer, mapped into this process
-        self.num_flags = slots * world + slots
+        self.num_flags = slots * world + slots + 1       # ready[slot, src] | ack[slot] | one scratch word (see collect)
         self.flags = symm_mem.empty((self.num_flags,), dtype=torch.int64, device="cuda")
         self.flags.zero_()
         self.fhdl = symm_mem.rendezvous(self.flags, group)
@@ -116,13 +116,26 @@ class PeerComposites:
                            signal_flag=self.ready_ptr(slot, self.rank), signal_value=n)
         return n
 
-    def collect(self, rast, slot: int, coll_stream):
-        """Rank 0, on a side stream: wait for every view of this use of the slot, then release the slot."""
+    def collect(self, rast, slot: int, coll_stream, consume=None):
+        """Rank 0, on a side stream: wait for every view of this use of the slot, [consume them,] then release the slot.
+
+        Without `consume` the slot is released by the same kernel that saw the last ready flag (one launch; what the
+        benchmarks do — they only need the composites to have ARRIVED). A caller that reads the views passes
+        `consume(views)`: it is called between a wait-only launch and an ack-only launch and must enqueue its reads on
+        `coll_stream`, so no producer can overwrite the slot before they are done. Returns the [world, H, W] views."""
         if self.rank != 0:
             return None
         coll_stream.wait_event(self.local_ready[slot])
-        if self.world > 1:
-            rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, self.uses[slot],
-                              [self.ack_ptr(slot, r) for r in range(1, self.world)], self.uses[slot])
+        n, views = self.uses[slot], self.buf[slot]
+        acks = [self.ack_ptr(slot, r) for r in range(1, self.world)]
+        if self.world > 1 and consume is None:
+            rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, n, acks, n)
+        elif self.world > 1:
+            scratch = self.flag_views[0].data_ptr() + 8 * (self.num_flags - 1)
+            rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, n, [scratch] * (self.world - 1), n)   # wait only
+            consume(views)
+            rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, 0, acks, n)                           # ack only
+        elif consume is not None:
+            consume(views)
         self.collected[slot].record(coll_stream)
-        return self.buf[slot]                   # [world, H, W] — all composites of this round
+        return views

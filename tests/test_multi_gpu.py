@@ -34,19 +34,24 @@ def _worker(rank, world, port, q):
     peers = sharding.PeerComposites(scene.height, scene.width, rank, world)
     sums = []
     got = []
-    for k in range(5):                         # more rounds than slots: exercises the ack / slot-reuse path
+    for k in range(7):                         # more rounds than slots: exercises the ack / slot-reuse path
         slot = k % peers.slots
         fb.clear(0xFF000000 + k, 0.0)
         rast.draw_meshlets(fb, gscene, node.meshlet_offset, node.meshlet_count, scene.object_to_clip(node))
         rast.resolve(fb, gscene, **uni)
         peers.send(fb, slot, stream)               # rank 1: ONE kernel = wait for the slot's ack, de-tile over NVLink, raise ready
-        views = peers.collect(rast, slot, comm)    # rank 0: ONE kernel = wait for rank 1's ready flag, ack the slot
+        # rank 0: wait for rank 1's ready flag, copy the views out ON THE COLLECT STREAM, only then ack the slot — rank 1
+        # runs ahead freely (no barrier in this loop), so a slot released too early would show up as a wrong checksum
+        kept = []
+        def consume(views):
+            with torch.cuda.stream(comm):
+                kept.append(views.clone())
+        peers.collect(rast, slot, comm, consume=consume if rank == 0 else None)
         local = fb.get_pixels(0)
         sums.append(int(local.astype(np.uint64).sum()))
         if rank == 0:
             comm.synchronize()
-            got.append([int(views[r].cpu().numpy().view(np.uint32).astype(np.uint64).sum()) for r in range(world)])
-        dist.barrier()                             # rank 0 has read the slot before anyone may overwrite it (the ack is already out)
+            got.append([int(kept[0][r].cpu().numpy().view(np.uint32).astype(np.uint64).sum()) for r in range(world)])
     all_sums = [None] * world
     dist.all_gather_object(all_sums, sums)
     torch.cuda.synchronize()
@@ -75,6 +80,6 @@ def test_peer_memory_composite_gather_world2():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for k in range(5):
+    for k in range(7):
         assert got[k] == [all_sums[r][k] for r in range(2)], f"round {k}: gathered composites differ from what the ranks rendered"
     assert all_sums[0] != all_sums[1]          # the two ranks really rendered different views
