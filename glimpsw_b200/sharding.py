@@ -56,6 +56,45 @@ def render_views_sharded(num_views: int, render_view: Callable[[int], "torch.Ten
     return out
 
 
+class SlotProtocol:
+    """The flow control of the composite exchange, as data: which flag a kernel waits for and which it raises.
+
+    Flags are use counts that only grow. Every rank holds the same array layout (only some entries are live on each):
+        ready[slot, src]  (index slot * world + src)      lives on rank 0, raised by src after its last store
+        ack[slot]         (index slots * world + slot)     lives on every producer, raised by rank 0's collect
+        scratch           (last index)                     sink of the wait-only collect launch
+    The n-th use of a slot by producer r: wait ack[slot] >= n - 1 (nothing for n = 1), store the view, raise
+    ready[slot, r] = n. The n-th collect of the slot on rank 0: wait ready[slot, r] >= n for all r, [consume,] raise
+    ack[slot] = n on every producer. tests/test_sharding_cpu.py runs this plan under random interleavings."""
+
+    def __init__(self, world: int, slots: int):
+        self.world, self.slots = world, slots
+        self.num_flags = slots * world + slots + 1
+        self.uses = [0] * slots
+
+    def ready_index(self, slot: int, src: int) -> int:
+        return slot * self.world + src
+
+    def ack_index(self, slot: int) -> int:
+        return self.slots * self.world + slot
+
+    @property
+    def scratch_index(self) -> int:
+        return self.num_flags - 1
+
+    def next_use(self, slot: int) -> int:
+        self.uses[slot] += 1
+        return self.uses[slot]
+
+    def send_plan(self, rank: int, slot: int, n: int):
+        """(wait_index | None, wait_value, signal_index, signal_value) for producer `rank`'s n-th use of `slot`."""
+        return (self.ack_index(slot) if n > 1 else None, n - 1, self.ready_index(slot, rank), n)
+
+    def collect_plan(self, slot: int, n: int):
+        """(ready indices on rank 0, expected value, ack index on each producer, ack value) for the n-th collect."""
+        return ([self.ready_index(slot, r) for r in range(1, self.world)], n, self.ack_index(slot), n)
+
+
 class PeerComposites:
     """Composite gather without a collective call: every rank's de-tile kernel (Framebuffer::GetPixels) stores
     its finished view straight into rank 0's buffer through NVLink peer memory, and the flow control rides in the
@@ -75,18 +114,19 @@ class PeerComposites:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.rank, self.world, self.slots = rank, world, slots
+        self.proto = SlotProtocol(world, slots)
         group = dist.group.WORLD.group_name
         self.buf = symm_mem.empty((slots, world, height, width), dtype=torch.int32, device="cuda")
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.root = self.hdl.get_buffer(0, self.buf.shape, self.buf.dtype)   # rank 0's buffer, mapped into this process
-        self.num_flags = slots * world + slots + 1       # ready[slot, src] | ack[slot] | one scratch word (see collect)
+        self.num_flags = self.proto.num_flags            # ready[slot, src] | ack[slot] | one scratch word (see SlotProtocol)
         self.flags = symm_mem.empty((self.num_flags,), dtype=torch.int64, device="cuda")
         self.flags.zero_()
         self.fhdl = symm_mem.rendezvous(self.flags, group)
         self.flag_views = [self.fhdl.get_buffer(r, self.flags.shape, self.flags.dtype) for r in range(world)]
         torch.cuda.synchronize()
         dist.barrier()                                   # every rank's flags are zero before anyone raises one
-        self.uses = [0] * slots
+        self.uses = self.proto.uses
         self.local_ready = [torch.cuda.Event() for _ in range(slots)]
         self.collected = [torch.cuda.Event() for _ in range(slots)]
 
@@ -95,25 +135,26 @@ class PeerComposites:
 
     def ready_ptr(self, slot: int, src: int) -> int:
         """ready[slot, src] in rank 0's memory."""
-        return self.flag_views[0].data_ptr() + 8 * (slot * self.world + src)
+        return self.flag_views[0].data_ptr() + 8 * self.proto.ready_index(slot, src)
 
     def ack_ptr(self, slot: int, owner: int) -> int:
         """ack[slot] in `owner`'s memory."""
-        return self.flag_views[owner].data_ptr() + 8 * (self.slots * self.world + slot)
+        return self.flag_views[owner].data_ptr() + 8 * self.proto.ack_index(slot)
 
     def send(self, fb, slot: int, comm_stream, layer: int = 0):
         """This rank's finished view -> root[slot, rank], on `comm_stream`. Returns the use count of the slot."""
-        self.uses[slot] += 1
-        n = self.uses[slot]
+        n = self.proto.next_use(slot)
         if self.rank == 0:
             if n > 1:
                 comm_stream.wait_event(self.collected[slot])
             fb.get_pixels_device(layer, self.dst_ptr(slot), cuda_stream=comm_stream.cuda_stream)
             self.local_ready[slot].record(comm_stream)
         else:
+            wait_index, wait_value, signal_index, signal_value = self.proto.send_plan(self.rank, slot, n)
+            mine, root = self.flag_views[self.rank].data_ptr(), self.flag_views[0].data_ptr()
             fb.send_pixels(layer, self.dst_ptr(slot), comm_stream.cuda_stream,
-                           wait_flag=self.ack_ptr(slot, self.rank) if n > 1 else 0, wait_value=n - 1,
-                           signal_flag=self.ready_ptr(slot, self.rank), signal_value=n)
+                           wait_flag=0 if wait_index is None else mine + 8 * wait_index, wait_value=wait_value,
+                           signal_flag=root + 8 * signal_index, signal_value=signal_value)
         return n
 
     def collect(self, rast, slot: int, coll_stream, consume=None):
@@ -131,7 +172,7 @@ class PeerComposites:
         if self.world > 1 and consume is None:
             rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, n, acks, n)
         elif self.world > 1:
-            scratch = self.flag_views[0].data_ptr() + 8 * (self.num_flags - 1)
+            scratch = self.flag_views[0].data_ptr() + 8 * self.proto.scratch_index
             rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, n, [scratch] * (self.world - 1), n)   # wait only
             consume(views)
             rast.peer_collect(coll_stream.cuda_stream, self.ready_ptr(slot, 1), self.world - 1, 0, acks, n)                           # ack only

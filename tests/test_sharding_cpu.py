@@ -52,3 +52,63 @@ def test_gather_world2_gloo(num_views):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert result == [v * 7 + 1 for v in range(num_views)]
+
+
+# ---- the flag protocol of the NVLink composite exchange (sharding.SlotProtocol), simulated ---------------------------
+@pytest.mark.parametrize("world,slots,frames,seed", [(2, 2, 9, 0), (4, 3, 10, 1), (8, 6, 14, 2), (3, 1, 6, 3)])
+def test_slot_protocol_under_random_interleavings(world, slots, frames, seed):
+    """Every rank renders `frames` views; producers (ranks >= 1) and the consumer (rank 0) advance in a random order,
+    each blocked exactly where its kernel would spin. The consumer must always find, in every slot it collects, the view
+    of THIS round from every producer (never an older or a newer one), and nobody may deadlock."""
+    import random
+    rng = random.Random(seed)
+    protos = [sharding.SlotProtocol(world, slots) for _ in range(world)]         # one per process, like the real thing
+    flags = [[0] * protos[0].num_flags for _ in range(world)]                     # flags[r] = rank r's copy of the array
+    data = [[None] * world for _ in range(slots)]                                 # rank 0's image buffer: data[slot][src] = frame index
+    pc = [0] * world                                                              # next frame of each rank
+    stage = ["send"] * world                                                      # rank 0 alternates send (local copy) / collect
+    collected = []
+    for _ in range(100000):
+        if all(p == frames for p in pc):
+            break
+        runnable = []
+        for r in range(world):
+            if pc[r] == frames:
+                continue
+            slot = pc[r] % slots
+            if r == 0:
+                if stage[0] == "send":
+                    runnable.append(r)                                            # local de-tile: ordered by events on rank 0 itself
+                else:
+                    ready, expected, _, _ = protos[0].collect_plan(slot, protos[0].uses[slot])
+                    if all(flags[0][i] >= expected for i in ready):
+                        runnable.append(r)
+            else:
+                n = protos[r].uses[slot] + 1
+                wait_index, wait_value, _, _ = protos[r].send_plan(r, slot, n)
+                if wait_index is None or flags[r][wait_index] >= wait_value:
+                    runnable.append(r)
+        assert runnable, f"deadlock at {pc}"
+        r = rng.choice(runnable)
+        slot = pc[r] % slots
+        if r == 0 and stage[0] == "send":
+            protos[0].next_use(slot)
+            data[slot][0] = pc[0]
+            stage[0] = "collect"
+        elif r == 0:
+            n = protos[0].uses[slot]
+            assert data[slot] == [pc[0]] * world, f"round {pc[0]}: slot {slot} holds {data[slot]}"
+            collected.append(pc[0])
+            _, _, ack_index, ack_value = protos[0].collect_plan(slot, n)
+            for p in range(1, world):
+                flags[p][ack_index] = ack_value                                   # st.release.sys into every producer's memory
+            stage[0] = "send"
+            pc[0] += 1
+        else:
+            n = protos[r].next_use(slot)
+            _, _, signal_index, signal_value = protos[r].send_plan(r, slot, n)
+            data[slot][r] = pc[r]                                                 # the de-tile stores, then the fence, then the flag
+            flags[0][signal_index] = signal_value
+            pc[r] += 1
+    assert collected == list(range(frames))
+    assert all(p == frames for p in pc)
