@@ -456,7 +456,7 @@ def cpu_frames(scene, node, uni, budget_s: float, max_frames: int, threads: int 
     timed = times[1:] if len(times) > 1 else times
     med = float(np.median(timed))
     out = {"value": round(scene.num_triangles / med / 1e6, 2), "unit": UNIT, "cores": base.threads, "kind": "port",
-           "isa": "avx512 (16-lane 4x4-fragment raster loop and resolve; per-vertex transform and per-triangle setup scalar)" if base.avx512 else "scalar (no AVX-512 on this host)",
+           "isa": "avx512 (16-lane vertex transform, 16-triangle packet classification + early setup, 4x4-fragment raster loop, resolve; per-triangle edge setup and binning scalar)" if base.avx512 else "scalar (no AVX-512 on this host)",
            "sample": f"{len(timed)} full frames of the same workload after 1 warm-up (median {med * 1e3:.1f} ms/frame)",
            "ms_per_step": round(med * 1e3, 3), "cpu": cpu_model()}
     base.close()

@@ -41,6 +41,10 @@ extern "C" void orc_resolve_rows_avx512(uint32_t* color, const float* depth, uin
                                  const float* objectToWorld3, const float* invScreenProj, const float* viewPos, float exposure,
                                  uint32_t yBegin, uint32_t yEnd);
 
+extern "C" uint32_t orc_meshlet_setup_avx512(const swr_meshlet* mesh, const float* M, float bx, float by, float fixX, float fixY,
+                                             int halfW, int halfH, int cullMode, float* nx, float* ny, float* nz, uint32_t* pos,
+                                             uint32_t* fl, uint32_t* keep, uint32_t* bbMin, uint32_t* bbMax);
+
 namespace {
 
 constexpr uint32_t kBinShift = 7, kBinSize = 1u << kBinShift;   // Rasterizer.cpp:15
@@ -246,6 +250,32 @@ void orc_mt_draw_meshlets(void* p, uint32_t* color, float* depth, uint32_t width
             nProc += primCount;
             int cullMode = SWR_CULL_FRONT_CCW;
             if (mesh.MaterialId != SWR_NO_MATERIAL && materials) cullMode = materials[mesh.MaterialId].IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
+            auto emit = [&](uint32_t prim, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t bbMin, uint32_t bbMax) {
+                Tri t;
+                t.pos0 = pos[i0]; t.pos1 = pos[i1]; t.pos2 = pos[i2];
+                t.bbMin = bbMin; t.bbMax = bbMax;
+                t.z0 = nz[i0]; t.z1 = nz[i1]; t.z2 = nz[i2];
+                t.id = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;
+                uint32_t ti = (uint32_t)tris.size();
+                tris.push_back(t);
+                // DistributeToBins (Rasterizer.cpp:664-695)
+                uint32_t bx0 = (t.bbMin & 0xFFFF) >> kBinShift, by0 = (t.bbMin >> 16) >> kBinShift;
+                uint32_t bx1 = ((t.bbMax & 0xFFFF) - 1) >> kBinShift, by1 = ((t.bbMax >> 16) - 1) >> kBinShift;
+                for (uint32_t byy = by0; byy <= by1; byy++)
+                    for (uint32_t bxx = bx0; bxx <= bx1; bxx++) bins[byy * binsX + bxx].push_back(ti);
+            };
+            if (pool.avx512) {           // 16 vertices / 16-triangle packets per step, like the reference (oracle/setup_avx512.cpp)
+                uint32_t keep[4];
+                alignas(64) uint32_t bbMinA[128], bbMaxA[128];
+                nClip += orc_meshlet_setup_avx512(&mesh, M, bx, by, fixX, fixY, halfW, halfH, cullMode, nx, ny, nz, pos, fl, keep, bbMinA, bbMaxA);
+                for (uint32_t w32 = 0; w32 < 4; w32++)
+                    for (uint32_t bitsLeft = keep[w32]; bitsLeft; bitsLeft &= bitsLeft - 1) {
+                        const uint32_t prim = w32 * 32 + (uint32_t)__builtin_ctz(bitsLeft);
+                        nRast++;
+                        emit(prim, mesh.Indices[0][prim] & 63, mesh.Indices[1][prim] & 63, mesh.Indices[2][prim] & 63, bbMinA[prim], bbMaxA[prim]);
+                    }
+                continue;
+            }
             uint32_t nv = std::min(((uint32_t)mesh.NumVertices + 15u) & ~15u, 64u);
             for (uint32_t v = 0; v < nv; v++) {          // ShadeMeshlet + per-vertex part of ComputeClipCodes / Setup
                 float x = mesh.Positions[0][v], y = mesh.Positions[1][v], z = mesh.Positions[2][v];
@@ -274,20 +304,11 @@ void orc_mt_draw_meshlets(void* p, uint32_t* color, float* depth, uint32_t width
                 float det = (nx[i2] - nx[i0]) * (ny[i1] - ny[i0]) - (nx[i0] - nx[i1]) * (ny[i0] - ny[i2]);
                 if (cullMode != SWR_CULL_FRONT_CCW) { bool flip = cullMode == SWR_CULL_FRONT_CW ? true : det < 0; det = flip ? -det : det; }
                 if (!(det > 0)) continue;
-                Tri t;
-                t.pos0 = pos[i0]; t.pos1 = pos[i1]; t.pos2 = pos[i2];
-                render_bbox(t.pos0, t.pos1, t.pos2, halfW, halfH, t.bbMin, t.bbMax);
-                if (lo16(t.bbMin) >= lo16(t.bbMax) || hi16(t.bbMin) >= hi16(t.bbMax)) continue;
+                uint32_t bbMin, bbMax;
+                render_bbox(pos[i0], pos[i1], pos[i2], halfW, halfH, bbMin, bbMax);
+                if (lo16(bbMin) >= lo16(bbMax) || hi16(bbMin) >= hi16(bbMax)) continue;
                 nRast++;
-                t.z0 = nz[i0]; t.z1 = nz[i1]; t.z2 = nz[i2];
-                t.id = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;
-                uint32_t ti = (uint32_t)tris.size();
-                tris.push_back(t);
-                // DistributeToBins (Rasterizer.cpp:664-695)
-                uint32_t bx0 = (t.bbMin & 0xFFFF) >> kBinShift, by0 = (t.bbMin >> 16) >> kBinShift;
-                uint32_t bx1 = ((t.bbMax & 0xFFFF) - 1) >> kBinShift, by1 = ((t.bbMax >> 16) - 1) >> kBinShift;
-                for (uint32_t byy = by0; byy <= by1; byy++)
-                    for (uint32_t bxx = bx0; bxx <= bx1; bxx++) bins[byy * binsX + bxx].push_back(ti);
+                emit(prim, i0, i1, i2, bbMin, bbMax);
             }
         }
         cProcessed += nProc; cRasterized += nRast; cClipped += nClip;
