@@ -19,6 +19,7 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -47,6 +48,7 @@ extern "C" uint32_t orc_meshlet_setup_avx512(const swr_meshlet* mesh, const floa
 
 namespace {
 
+double g_phaseMs[2] = { 0, 0 };
 constexpr uint32_t kBinShift = 7, kBinSize = 1u << kBinShift;   // Rasterizer.cpp:15
 
 struct Tri {                 // TrianglePacket lane (Rasterizer.h:145-161)
@@ -232,6 +234,7 @@ void orc_mt_draw_meshlets(void* p, uint32_t* color, float* depth, uint32_t width
     std::atomic<uint64_t> cProcessed{0}, cRasterized{0}, cClipped{0};
 
     // ---- phase 1: mesh shading + setup + binning; worker w owns a contiguous meshlet range
+    const auto tPhase0 = std::chrono::steady_clock::now();
     pool.run([&](uint32_t w) {
         auto& tris = pool.tris[w];
         auto& bins = pool.bins[w];
@@ -315,6 +318,7 @@ void orc_mt_draw_meshlets(void* p, uint32_t* color, float* depth, uint32_t width
     });
 
     // ---- phase 2: RasterizeBin (Rasterizer.cpp:696-739); bins handed out dynamically, worker lists in order
+    const auto tPhase1 = std::chrono::steady_clock::now();
     std::atomic<uint32_t> nextBin{0};
     pool.run([&](uint32_t) {
         for (;;) {
@@ -337,7 +341,13 @@ void orc_mt_draw_meshlets(void* p, uint32_t* color, float* depth, uint32_t width
         }
     });
     counters[0] += cProcessed; counters[1] += cRasterized; counters[2] += cClipped;
+    const auto tPhase2 = std::chrono::steady_clock::now();
+    g_phaseMs[0] = std::chrono::duration<double, std::milli>(tPhase1 - tPhase0).count();
+    g_phaseMs[1] = std::chrono::duration<double, std::milli>(tPhase2 - tPhase1).count();
 }
+
+// Wall time of the two phases of the last orc_mt_draw_meshlets call (setup + binning, bin rasterization), for profiling the baseline.
+void orc_mt_phase_ms(double out[2]) { out[0] = g_phaseMs[0]; out[1] = g_phaseMs[1]; }
 
 // ShadingContext::Resolve split by rows of 32 px (Rasterizer::DispatchPass, Rasterizer.h:225-242).
 void orc_mt_resolve(void* p, uint32_t* color, const float* depth, uint32_t width, uint32_t height,
