@@ -452,6 +452,26 @@ def closeup_alpha_scene(width: int = 960, height: int = 540, nu: int = 40, nv: i
     return scene
 
 
+def patchwork_scene(patches_x: int = 40, patches_y: int = 32, width: int = 1280, height: int = 720, num_materials: int = 9,
+                    seed: int = 31) -> SceneData:
+    """The heightfield grid with a different material on (almost) every neighbouring meshlet: `num_materials` materials with
+    textures from 32^2 to 512^2 texels, every other one without a normal / metallic-roughness layer, one without any
+    texture-bound material at all (MaterialId = UINT_MAX). Most 4x4 fragments along meshlet borders then hold several
+    materials with different mip decisions — the per-fragment material waterfall and filter votes of ResolveSurface
+    (Shading.cpp:532-545, Texture.h:432) at their worst."""
+    from . import textures as tx
+    scene = grid_scene(patches_x, patches_y, width, height, seed=seed, material_id=0)
+    pick = (splitmix64(seed, len(scene.meshlets)) % np.uint64(num_materials + 1)).astype(np.int64)
+    scene.meshlets["MaterialId"] = np.where(pick == num_materials, NO_MATERIAL, pick).astype(np.uint32)
+    scene.materials = np.zeros(num_materials, dtype=MATERIAL_DTYPE)
+    scene.materials["AlphaCutoff"] = 255
+    scene.materials["TextureId"] = np.arange(num_materials)
+    scene.textures = [tx.procedural_material_texture(32 << (k % 5), seed=seed + k, with_nmr=(k % 2 == 0)) for k in range(num_materials)]
+    scene.lights = np.concatenate([default_light(), make_light(1, position=(2.5, 4.0, 1.0), color=(1.0, 0.6, 0.3), intensity=60.0, radius=9.0)])
+    scene.name = f"patchwork{patches_x}x{patches_y}"
+    return scene
+
+
 def resolve_uniforms(scene: SceneData, node: DrawNode, exposure: float = 1.0) -> dict:
     """The ShadingContext fields Resolve reads (Shading.h:21-33, Shading.cpp:659)."""
     proj, view = scene.view_proj()

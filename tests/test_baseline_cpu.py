@@ -62,3 +62,27 @@ def test_mt_baseline_equals_scalar_on_ragged_meshlets(orc, seed, spread):
     assert np.array_equal(fb.data[:, :n], fb2.data[:, :n]) and list(c[:3]) == list(c2[:3])
     assert int(c[0]) == int(meshlets["NumTriangles"].astype(np.int64).sum()) and int(c[2]) > 0
     base.close()
+
+
+def test_mt_baseline_resolve_equals_scalar_on_many_materials(orc):
+    """scenes.patchwork_scene: nine materials (textures 32^2..512^2, with and without a normal / metal-rough layer) plus
+    material-less meshlets, two lights; a fifth of the 4x4 fragments hold several materials. The 16-lane resolve with its
+    scalar material waterfall must still equal the scalar spec bit for bit."""
+    scene = scenes.patchwork_scene()
+    node = scene.nodes[0]
+    m, uni = scene.object_to_clip(node), scenes.resolve_uniforms(scene, node)
+    n = scene.width * scene.height
+    fb = orc.Framebuffer(scene.width, scene.height)
+    fb.clear(0xFF000000, 0.0)
+    orc.draw_meshlets(fb, scene.meshlets, 0, len(scene.meshlets), m, materials=scene.materials)
+    ids, depth = fb.data[0, :n].copy(), fb.data[1, :n].view(np.float32)
+    mats = np.where(depth > 0, scene.meshlets["MaterialId"][np.minimum(ids // 128, len(scene.meshlets) - 1)], 0xFFFFFFFE).reshape(-1, 16)
+    assert np.mean([len(set(f.tolist()) - {0xFFFFFFFE}) >= 2 for f in mats[::11]]) > 0.1      # the scene does what it says
+    orc.resolve(fb, scene.meshlets, scene.materials, scene.textures, scene.lights, **uni)
+    base = orc.Baseline(3)
+    fb2 = orc.Framebuffer(scene.width, scene.height)
+    base.clear(fb2, 0xFF000000, 0.0)
+    base.draw_meshlets(fb2, scene.meshlets, 0, len(scene.meshlets), m, materials=scene.materials)
+    base.resolve(fb2, scene.meshlets, scene.materials, scene.textures, scene.lights, **uni)
+    assert np.array_equal(fb.data[:, :n], fb2.data[:, :n])
+    base.close()

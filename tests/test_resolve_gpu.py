@@ -51,6 +51,20 @@ def test_resolve_point_and_spot_lights(orc, rast_factory):
     assert max_abs <= MAX_ABS and psnr >= MIN_PSNR, f"max abs {max_abs}/255, PSNR {psnr:.1f} dB, {frac:.4%} pixels differ"
 
 
+def test_resolve_many_materials_per_fragment(orc, rast_factory):
+    """scenes.patchwork_scene: a fifth of the 4x4 fragments hold two or more of nine materials with different texture
+    sizes / layer counts (plus material-less meshlets): the half-warp material waterfall and its per-fragment filter votes."""
+    scene = scenes.patchwork_scene()
+    (max_abs, psnr, frac), _, _ = run_scene(orc, rast_factory(), scene)
+    assert max_abs <= MAX_ABS and psnr >= MIN_PSNR, f"max abs {max_abs}/255, PSNR {psnr:.1f} dB, {frac:.4%} pixels differ"
+    # and through the clip-cached path (no read-back between draw and resolve)
+    cached, _ = _frame(rast_factory(), scene)
+    ofb, _ = oracle_render(orc, scene)
+    orc.resolve(ofb, scene.meshlets, scene.materials, scene.textures, scene.lights, **scenes.resolve_uniforms(scene, scene.nodes[0]))
+    max_abs, psnr, frac = color_error(ofb.data[0, :scene.width * scene.height], cached.download_tiled(0))
+    assert max_abs <= MAX_ABS and psnr >= MIN_PSNR
+
+
 def test_resolve_untextured_grid(orc, rast_factory):
     """Material-less meshlets (MaterialId == UINT_MAX) shade with albedo 0 -> tonemapped black, still in tolerance."""
     scene = scenes.grid_scene(24, 20, 640, 480, seed=9)
