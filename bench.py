@@ -150,6 +150,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    full_affinity = os.sched_getaffinity(0)
     bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version banner under
@@ -393,6 +394,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only): the reference restatement on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, full_affinity)          # the CPU baseline gets every host core, not just the GPU's NUMA node
         cpu = cpu_frames(scene, node, uni, budget_s=args.cpu_budget, max_frames=40)
 
     if rank == 0:
