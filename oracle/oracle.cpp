@@ -55,6 +55,7 @@ inline Vec4 mul_mat4_pos(const float* m, float x, float y, float z) {
 // with FMAs, numerator multiplied afterwards) so tools/rcp14_sensitivity.py can measure how far such a binary would be
 // from the canonical IEEE arithmetic (mode 0, the default, the only mode parity is defined against).
 int g_rcpMode = 0;
+int g_contractDet = 0;       // sensitivity only: the cull determinant as fma(a, b, -(c * d)), the contraction -ffast-math allows (App. B.1b)
 __attribute__((target("avx512f"))) inline float rcp14_nr(float x) {
     float e = _mm_cvtss_f32(_mm_rcp14_ss(_mm_setzero_ps(), _mm_set_ss(x)));
     return std::fmaf(std::fmaf(-x, e, 1.0f), e, e);
@@ -110,6 +111,7 @@ inline int tri_setup(Vec4 v0, Vec4 v1, Vec4 v2, int halfW, int halfH, int cullMo
 
     // :262 (canonical: every product rounded, then the subtraction)
     float det = (v2.x - v0.x) * (v1.y - v0.y) - (v0.x - v1.x) * (v0.y - v2.y);
+    if (g_contractDet) det = std::fmaf(v2.x - v0.x, v1.y - v0.y, -((v0.x - v1.x) * (v0.y - v2.y)));
     if (cullMode != SWR_CULL_FRONT_CCW) {                                    // :264-267
         bool flip = (cullMode == SWR_CULL_FRONT_CW) ? true : (det < 0);
         det = flip ? -det : det;
@@ -600,8 +602,9 @@ uint32_t orc_cull_meshlets(uint16_t* bitmap, const swr_meshlet* meshlets, uint32
 // 0 = canonical IEEE division (default); 1 = vrcp14ps + one Newton-Raphson step (sensitivity study only).
 // Returns -1 (mode unchanged) when the host CPU has no AVX-512F.
 int orc_set_reciprocal_mode(int mode) {
-    if (mode != 0 && !__builtin_cpu_supports("avx512f")) return -1;
-    g_rcpMode = mode != 0;
+    if ((mode & 1) && !__builtin_cpu_supports("avx512f")) return -1;
+    g_rcpMode = mode & 1;
+    g_contractDet = (mode >> 1) & 1;        // bit 1: contract the cull determinant into one FMA
     return 0;
 }
 

@@ -278,7 +278,8 @@ def probe_triangle(verts, width: int, height: int, cull_mode: int = 1, guardband
 
 
 def set_reciprocal_mode(mode: int) -> bool:
-    """0 = canonical IEEE division (default, what parity is defined against); 1 = vrcp14ps + one Newton-Raphson step, the
-    code clang most likely emits for the reference's -ffast-math vector divisions. Sensitivity studies
-    only (tools/rcp14_sensitivity.py). Returns False when the host has no AVX-512F (mode unchanged)."""
+    """0 = canonical arithmetic (default, what parity is defined against). Bit 0: vrcp14ps + one Newton-Raphson step instead
+    of IEEE division, the code clang most likely emits for the reference's -ffast-math vector divisions (SURVEY App. B.1a);
+    bit 1: the back-face determinant contracted into one FMA (App. B.1b). Sensitivity studies only
+    (tools/rcp14_sensitivity.py). Returns False when bit 0 is asked for on a host without AVX-512F (mode unchanged)."""
     return lib().orc_set_reciprocal_mode(C.c_int(mode)) == 0

@@ -234,6 +234,8 @@ def test_rcp14_newton_sensitivity_is_confined_to_depth_ulps(orc):
         r = rcp14_sensitivity.compare(scene, cull)
         assert r["ids_differ"] == 0 and r["coverage_differs"] == 0 and r["counters_ieee"] == r["counters_rcp14_nr"]
         assert 0 < r["depth_words_differ"] < 0.01 * r["covered"] and r["max_depth_ulp"] <= 4
+        c = rcp14_sensitivity.compare(scene, cull, mode=2)        # the cull determinant contracted into one FMA (App. B.1b)
+        assert c["counters_ieee"] == c["counters_rcp14_nr"] and c["ids_differ"] == 0 and c["depth_words_differ"] == 0
     # the switch is off again: the canonical mode is what every other test runs in
     fb, _ = oracle_render(orc, scenes.grid_scene(20, 16, 640, 360, seed=3, flip_fraction=0.2))
     import hashlib, json

@@ -24,10 +24,11 @@ from oracle import orc  # noqa: E402
 from helpers import oracle_render  # noqa: E402
 
 
-def compare(scene, cull=False):
+def compare(scene, cull=False, mode=1):
+    """mode: bit 0 = rcp14 + Newton reciprocals, bit 1 = contracted cull determinant (oracle.orc.set_reciprocal_mode)."""
     n = scene.width * scene.height
     out = []
-    for mode in (0, 1):
+    for mode in (0, mode):
         if not orc.set_reciprocal_mode(mode):
             raise SystemExit("this host has no AVX-512F: cannot execute vrcp14ss")
         fb, counters = oracle_render(orc, scene, cull=cull)
@@ -44,10 +45,14 @@ def compare(scene, cull=False):
 
 if __name__ == "__main__":
     orc.build()
-    report = {
-        "c2_grid_1M_1080p": compare(scenes.grid_scene()),
-        "c1_knot_72k_1080p": compare(scenes.torus_knot_scene()),
-        "c4_small_instanced_720p": compare(scenes.instanced_scene(subdivisions=4, instances=27, width=1280, height=720), cull=True),
-        "room_big_triangles_1080p": compare(scenes.room_scene()),
+    cases = {
+        "c2_grid_1M_1080p": (scenes.grid_scene, False),
+        "c1_knot_72k_1080p": (scenes.torus_knot_scene, False),
+        "c4_small_instanced_720p": (lambda: scenes.instanced_scene(subdivisions=4, instances=27, width=1280, height=720), True),
+        "room_big_triangles_1080p": (scenes.room_scene, False),
     }
+    report = {}
+    for name, (make, cull) in cases.items():
+        report[name] = {"rcp14_newton": compare(make(), cull, 1), "contracted_determinant": compare(make(), cull, 2),
+                        "both": compare(make(), cull, 3)}
     print(json.dumps(report, indent=1))
