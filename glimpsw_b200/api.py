@@ -52,10 +52,11 @@ EXPORTS = [
     "swrb_fb_get_pixels_async", "swrb_hiz_create", "swrb_hiz_destroy", "swrb_hiz_info", "swrb_hiz_build",
     "swrb_hiz_download", "swrb_cull_meshlets_hiz", "swrb_draw_batch_program", "swrb_resolve_debug",
     "swrb_fb_send_pixels", "swrb_peer_collect", "swrb_device_set_mesh_occupancy",
-    "swrb_scene_set_skybox",
+    "swrb_scene_set_skybox", "swrb_batch_create", "swrb_batch_destroy", "swrb_draw_prepared", "swrb_frame_submit",
+    "swrb_scene_meshlets_device", "swrb_scene_touch",
 ]
 
-PROGRAM_VISBUFFER, PROGRAM_OVERDRAW = 0, 1     # ShadingContext::VisBufferShader / OverdrawShader (Shading.h:49)
+PROGRAM_VISBUFFER, PROGRAM_OVERDRAW, PROGRAM_DEFERRED = 0, 1, 2   # ShadingContext::VisBufferShader / OverdrawShader / DeferredShader (Shading.h:49)
 # enum class DebugLayer (Shading.h:8)
 DEBUG_LAYERS = ["None", "BaseColor", "Normals", "MetallicRoughness", "MeshletId", "TriangleId", "OverdrawPixel", "OverdrawQuad"]
 
@@ -66,7 +67,8 @@ class SwrbError(RuntimeError):
 
 class DrawDesc(C.Structure):
     _fields_ = [("MeshletOffset", C.c_uint32), ("MeshletCount", C.c_uint32), ("ObjectToClip", C.c_float * 16),
-                ("CullBitmapHost", C.c_void_p), ("UseDeviceCullBitmap", C.c_int32), ("FrustumPlanes", C.c_float * 20)]
+                ("CullBitmapHost", C.c_void_p), ("UseDeviceCullBitmap", C.c_int32), ("FrustumPlanes", C.c_float * 20),
+                ("ObjectToWorld", C.c_float * 9)]
 
 
 class ShadingUniforms(C.Structure):
@@ -82,6 +84,12 @@ class TextureDesc(C.Structure):
 
 class PeerSync(C.Structure):     # swrb_peer_sync
     _fields_ = [("WaitFlag", C.c_void_p), ("WaitValue", C.c_uint64), ("SignalFlag", C.c_void_p), ("SignalValue", C.c_uint64)]
+
+
+class FrameDesc(C.Structure):    # swrb_frame_desc
+    _fields_ = [("ClearColor", C.c_uint32), ("ClearDepth", C.c_float), ("Batch", C.c_void_p), ("Uniforms", C.c_void_p),
+                ("PixelsDevice", C.c_void_p), ("PixelsStride", C.c_uint32), ("PixelsStream", C.c_void_p),
+                ("PeerSync", C.c_void_p), ("PixelsHost", C.c_void_p)]
 
 
 class FbInfo(C.Structure):
@@ -107,8 +115,11 @@ def load_library() -> C.CDLL:
         lib.swrb_scene_destroy.restype = None
         lib.swrb_fb_destroy.restype = None
         lib.swrb_hiz_destroy.restype = None
-        for name in ("swrb_device_destroy", "swrb_scene_destroy", "swrb_fb_destroy", "swrb_hiz_destroy"):
+        lib.swrb_batch_destroy.restype = None
+        for name in ("swrb_device_destroy", "swrb_scene_destroy", "swrb_fb_destroy", "swrb_hiz_destroy", "swrb_batch_destroy"):
             getattr(lib, name).argtypes = [C.c_void_p]
+        lib.swrb_frame_submit.argtypes = [C.c_void_p, C.c_void_p]
+        lib.swrb_draw_prepared.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.swrb_device_reserve.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         _lib = lib
     return _lib
@@ -243,9 +254,41 @@ class Scene:
         meshlets = np.ascontiguousarray(meshlets)
         _check(self.rast.lib.swrb_scene_update_meshlets(self._h, _ptr(meshlets), C.c_uint32(first), C.c_uint32(len(meshlets))))
 
+    def meshlets_device_ptr(self) -> int:
+        """Device address of the scene's meshlet array (num_meshlets x 1728 bytes), for callers that fill it on the device."""
+        p = C.c_void_p()
+        _check(self.rast.lib.swrb_scene_meshlets_device(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def touch(self, first: int = 0, count: int | None = None):
+        """Declares meshlets [first, first + count) rewritten on the device (derived tables are rebuilt lazily)."""
+        _check(self.rast.lib.swrb_scene_touch(self._h, C.c_uint32(first), C.c_uint32(self.num_meshlets - first if count is None else count)))
+
     def destroy(self):
         if self._h:
             self.rast.lib.swrb_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Batch:
+    """swrb_batch: a prepared list of DrawMeshlets calls (one per glTF node, Main.cpp:216-240) living on the device."""
+
+    def __init__(self, rast: "Rasterizer", scene: Scene, draws: list):
+        self.rast, self.scene = rast, scene
+        arr, n, keep = rast.make_batch(draws)
+        self._h = C.c_void_p()
+        _check(rast.lib.swrb_batch_create(scene._h, arr, C.c_uint32(n), C.byref(self._h)))
+        rast._children.add(self)
+
+    def destroy(self):
+        if self._h:
+            self.rast.lib.swrb_batch_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -354,10 +397,12 @@ class Rasterizer:
         return out
 
     @staticmethod
-    def _desc(offset, count, object_to_clip, cull_bitmap=None, use_device_bitmap=False, planes=None, keep=None) -> DrawDesc:
+    def _desc(offset, count, object_to_clip, cull_bitmap=None, use_device_bitmap=False, planes=None, keep=None,
+              object_to_world3=None) -> DrawDesc:
         d = DrawDesc()
         d.MeshletOffset, d.MeshletCount = offset, count
         d.ObjectToClip[:] = _mat(object_to_clip).tolist()
+        d.ObjectToWorld[:] = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0] if object_to_world3 is None else _mat(object_to_world3).tolist()
         if cull_bitmap is not None:
             cb = np.ascontiguousarray(cull_bitmap, dtype=np.uint16)
             if keep is not None:
@@ -382,7 +427,7 @@ class Rasterizer:
         arr = (DrawDesc * len(draws))()
         for i, dd in enumerate(draws):
             arr[i] = self._desc(dd["offset"], dd["count"], dd["object_to_clip"], dd.get("cull_bitmap"),
-                                dd.get("use_device_bitmap", False), dd.get("planes"), keep)
+                                dd.get("use_device_bitmap", False), dd.get("planes"), keep, dd.get("object_to_world3"))
         if program == PROGRAM_VISBUFFER:
             _check(self.lib.swrb_draw_batch(fb._h, scene._h, arr, C.c_uint32(len(draws))))
         else:
@@ -394,8 +439,34 @@ class Rasterizer:
         arr = (DrawDesc * len(draws))()
         for i, dd in enumerate(draws):
             arr[i] = self._desc(dd["offset"], dd["count"], dd["object_to_clip"], dd.get("cull_bitmap"),
-                                dd.get("use_device_bitmap", False), dd.get("planes"), keep)
+                                dd.get("use_device_bitmap", False), dd.get("planes"), keep, dd.get("object_to_world3"))
         return arr, len(draws), keep
+
+    def create_batch(self, scene: Scene, draws: list) -> "Batch":
+        """swrb_batch_create: the frame's DrawMeshlets calls validated and uploaded once (same dict form as draw_batch)."""
+        return Batch(self, scene, draws)
+
+    def draw_prepared(self, fb: Framebuffer, batch: "Batch", program: int = PROGRAM_VISBUFFER):
+        _check(self.lib.swrb_draw_prepared(fb._h, batch._h, C.c_uint32(program)))
+
+    def make_frame(self, batch: "Batch", uniforms: ShadingUniforms | None, clear_color: int = 0xFF000000, clear_depth: float = 0.0,
+                   pixels_device: int = 0, pixels_stream: int = 0, pixels_host: np.ndarray | None = None, peer_sync: PeerSync | None = None,
+                   pixels_stride: int = 0) -> FrameDesc:
+        """A swrb_frame_desc (Clear -> batch -> Resolve -> GetPixels); build once per view, submit every frame."""
+        f = FrameDesc()
+        f.ClearColor, f.ClearDepth, f.Batch = clear_color, clear_depth, batch._h
+        f.Uniforms = C.cast(C.pointer(uniforms), C.c_void_p) if uniforms is not None else None
+        f.PixelsDevice, f.PixelsStride, f.PixelsStream = pixels_device or None, pixels_stride, pixels_stream or None
+        f.PeerSync = C.cast(C.pointer(peer_sync), C.c_void_p) if peer_sync is not None else None
+        f.PixelsHost = pixels_host.ctypes.data if pixels_host is not None else None
+        f._keep = (batch, uniforms, peer_sync, pixels_host)
+        return f
+
+    def submit_frame(self, fb: Framebuffer, frame: FrameDesc):
+        """swrb_frame_submit: one iteration of the reference's frame loop (Main.cpp:213-252) in one call."""
+        rc = self.lib.swrb_frame_submit(fb._h, C.addressof(frame))
+        if rc:
+            _check(rc)
 
     def draw_prebuilt(self, fb: Framebuffer, scene: Scene, batch):
         _check(self.lib.swrb_draw_batch(fb._h, scene._h, batch[0], C.c_uint32(batch[1])))
@@ -496,7 +567,7 @@ class Rasterizer:
 
     def destroy(self):
         if self._h:
-            for child in list(self._children):
+            for child in sorted(self._children, key=lambda c: 0 if isinstance(c, Batch) else 1):   # batches before their scenes
                 child.destroy()
             for ptr in self._pinned:
                 self.lib.swrb_free_pinned(self._h, ptr)

@@ -38,8 +38,8 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
         float4 ruv0 = make_float4(0.0f, 1.0f, 0.0f, 0.0f), ruv1 = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
         if (clipped) { ruv0 = __ldg(clipRemap + 2 * it); ruv1 = __ldg(clipRemap + 2 * it + 1); }
 
-        const swr_meshlet* mesh = meshlets + (t.id / SWR_MAX_PRIMS);
-        const uint32_t prim = t.id % SWR_MAX_PRIMS;
+        const swr_meshlet* mesh = meshlets + rank_meshlet(t.id);
+        const uint32_t prim = rank_prim(t.id);
         float uv[3][2];
 #pragma unroll
         for (int k = 0; k < 3; k++) {                                                 // UnpackHalf2x16 of TexCoords[VertexId[k]]

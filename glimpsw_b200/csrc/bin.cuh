@@ -7,8 +7,12 @@
 //                    into shared memory by itself — redundant but free of a launch and of a global sync;
 //                    block 0 also publishes the offsets and the list of non-empty tiles;
 //   pass 3 (scatter) writes compact per-tile triangle lists with warp ballots / match_any.
-// Triangles overlapping more than kBigTriTileLimit tiles are not expanded: they sit in a short "big"
-// list every active tile walks. Only triangles too large for the mesh kernel's inline raster get here.
+// Triangles overlapping more than kBigTriTileLimit tiles are not expanded per tile: they are listed per
+// 256 x 256-px SUPER-TILE (8 x 8 tiles; at most 12 x 12 = 144 of them at the 2896-px limit) with the same
+// count / scan / scatter, and a tile walks its own list plus its super-tile's. A screen-filling triangle then
+// costs 40 list entries at 1080p instead of 2,040, and a tile only meets the wide triangles near it (round 1
+// kept ONE frame-wide big list that every tile walked: any wide triangle made every tile active).
+// Only triangles too large for the mesh kernel's inline raster get here.
 #pragma once
 
 #include "common.cuh"
@@ -62,33 +66,57 @@ __device__ __forceinline__ void block_exclusive_scan_smem(uint32_t* s, uint32_t 
     __syncthreads();
 }
 
+constexpr uint32_t kMaxSuperTiles = 144;     // ceil(2896 / 256)^2
+
+struct BinBuffers {                          // per device, sized for the framebuffer's tile grid
+    uint32_t* tileCount;  uint32_t* tileOffset;  uint32_t* tileCursor;  uint32_t* activeTiles;
+    uint32_t* superCount; uint32_t* superOffset; uint32_t* superCursor;   // kMaxSuperTiles (+1) words each
+    uint32_t* binEntries; uint32_t binCapacity;
+    uint32_t* superEntries; uint32_t superCapacity;
+};
+
 // Passes 2 + 3. Dynamic shared memory: (numTiles + 1) * 4 bytes.
 __global__ void __launch_bounds__(kScatterThreads)
-k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, const uint32_t* __restrict__ tileCount,
-              uint32_t* __restrict__ tileOffset, uint32_t* __restrict__ tileCursor, uint32_t* __restrict__ activeTiles,
-              uint32_t* __restrict__ binEntries, uint32_t binCapacity, DevCtl* __restrict__ ctl) {
+k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, BinBuffers bb, DevCtl* __restrict__ ctl) {
     extern __shared__ uint32_t sOffset[];
     __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t sSuper[kMaxSuperTiles + 1];
+    const uint32_t* __restrict__ tileCount = bb.tileCount;
+    uint32_t* __restrict__ tileOffset = bb.tileOffset; uint32_t* __restrict__ tileCursor = bb.tileCursor;
+    uint32_t* __restrict__ activeTiles = bb.activeTiles; uint32_t* __restrict__ binEntries = bb.binEntries;
+    const uint32_t binCapacity = bb.binCapacity;
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
+    const uint32_t sh = kSuperShift - kTileShift, superX = (fp.tilesX + (1u << sh) - 1u) >> sh;
+    const uint32_t numSuper = superX * ((fp.tilesY + (1u << sh) - 1u) >> sh);
     const uint32_t n = ctl->overflow ? 0u : ctl->triCount;
     if (n == 0) return;     // no records (every triangle was rasterized inline): k_frame_begin left binTotal / numActiveTiles at 0,
                             // which is all the tile rasterizer looks at before it returns
 
     // ---- pass 2: counts (L2, produced by the mesh kernel's atomics) -> exclusive offsets in shared memory
     for (uint32_t i = threadIdx.x; i < numTiles; i += kScatterThreads) sOffset[i] = __ldcg(tileCount + i);
+    for (uint32_t i = threadIdx.x; i < numSuper; i += kScatterThreads) sSuper[i] = __ldcg(bb.superCount + i);
     __syncthreads();
     if (blockIdx.x == 0) {     // publish the tiles the tile rasterizer has to visit (before the counts are overwritten):
-        const bool allActive = ctl->bigCount != 0;   // big-list triangles are walked by every tile
-        for (uint32_t i = threadIdx.x; i < numTiles; i += kScatterThreads)
-            if (allActive || sOffset[i] != 0) activeTiles[atomicAdd(&ctl->numActiveTiles, 1u)] = i;
+        for (uint32_t i = threadIdx.x; i < numTiles; i += kScatterThreads) {   // its own list or its super-tile's is non-empty
+            const uint32_t tx = i % fp.tilesX, ty = i / fp.tilesX;
+            if (sOffset[i] != 0 || sSuper[(ty >> sh) * superX + (tx >> sh)] != 0) activeTiles[atomicAdd(&ctl->numActiveTiles, 1u)] = i;
+        }
         __syncthreads();
     }
     block_exclusive_scan_smem(sOffset, numTiles, warpSums);
-    const bool overflow = sOffset[numTiles] > binCapacity;
+    if (threadIdx.x == 0) {    // at most 144 super-tiles: a serial scan is a few hundred cycles
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < numSuper; i++) { const uint32_t c = sSuper[i]; sSuper[i] = run; run += c; }
+        sSuper[numSuper] = run;
+    }
+    __syncthreads();
+    const bool overflow = sOffset[numTiles] > binCapacity || sSuper[numSuper] > bb.superCapacity;
     if (blockIdx.x == 0) {
         for (uint32_t i = threadIdx.x; i <= numTiles; i += kScatterThreads) tileOffset[i] = sOffset[i];
+        for (uint32_t i = threadIdx.x; i <= numSuper; i += kScatterThreads) bb.superOffset[i] = sSuper[i];
         if (threadIdx.x == 0) {
             ctl->binTotal = sOffset[numTiles];
+            ctl->superTotal = sSuper[numSuper];
             if (overflow) atomicExch(&ctl->overflow, 3u);
         }
     }
@@ -118,7 +146,14 @@ k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, const uint32_t
             if (lane == leader) slot = atomicAdd(&tileCursor[tile], (uint32_t)__popc(peers));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
             binEntries[sOffset[tile] + slot] = i;
-        } else if (nTiles > 1 && nTiles <= (uint32_t)kBigTriTileLimit) {
+        } else if (nTiles > (uint32_t)kBigTriTileLimit) {
+            for (uint32_t sy = ty0 >> sh; sy <= (ty1 >> sh); sy++)
+                for (uint32_t sx = tx0 >> sh; sx <= (tx1 >> sh); sx++) {
+                    const uint32_t st = sy * superX + sx;
+                    const uint32_t slot = atomicAdd(&bb.superCursor[st], 1u);
+                    bb.superEntries[sSuper[st] + slot] = i;
+                }
+        } else if (nTiles > 1) {
             for (uint32_t ty = ty0; ty <= ty1; ty++)
                 for (uint32_t tx = tx0; tx <= tx1; tx++) {
                     uint32_t tl = ty * fp.tilesX + tx;

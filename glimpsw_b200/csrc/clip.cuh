@@ -92,7 +92,7 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
         }
         if (vertCount < 3) continue;                                            // :448 (+ empty fan for 2 vertices)
 
-        const uint32_t id = meshletId * SWR_MAX_PRIMS + prim;
+        const uint32_t id = key_rank(meshletId, prim, 1u);      // pieces are drawn after the packet's accepted lanes (Rasterizer.cpp:209-249)
         for (uint32_t vi = 0; vi + 2 < vertCount; vi++) {                       // :451-466, then FlushPacket -> Setup
             const uint32_t ix[3] = { indices[0], indices[vi + 1], indices[vi + 2] };
             float nx[3], ny[3], nz[3], rw[3];

@@ -18,17 +18,32 @@ k_fb_clear(uint4* __restrict__ layerA, uint32_t valueA, uint4* __restrict__ laye
     }
 }
 
+// The draw's transient device state: per-tile / per-super-tile counters and cursors and the work counters in
+// DevCtl (everything but `overflow`, which stays sticky until the host reads it, and the perf counters). The sizes
+// of the draw that just finished are kept in ctl->last* for swrb_get_draw_stats. Called by thread `gid` of `stride`.
+__device__ __forceinline__ void reset_draw_state(uint32_t gid, uint32_t stride, uint32_t* tileCount, uint32_t* tileCursor, uint32_t numTiles,
+                                                 uint32_t* superCount, uint32_t* superCursor, DevCtl* ctl) {
+    if (gid == 0) {
+        ctl->lastTriCount = ctl->triCount; ctl->lastBigCount = ctl->bigCount; ctl->lastBinTotal = ctl->binTotal + ctl->superTotal;
+        ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0;
+        ctl->workCursor = 0; ctl->superTotal = 0;
+    }
+    for (uint32_t i = gid; i < numTiles; i += stride) { tileCount[i] = 0; tileCursor[i] = 0; }
+    for (uint32_t i = gid; i < 160u; i += stride) { superCount[i] = 0; superCursor[i] = 0; }
+}
+
 // Start of a draw: seed the key buffer and reset the draw's transient device state in one launch.
 // keys <- (depth << 32 | seed), where depth is the pixel's stored depth (depthLayer != null) or the
 // pending clear's depth. A pixel keeps its seed unless a fragment of THIS draw passes the strict depth
-// test, so earlier draws win ties like in the reference. Also zeroes the per-tile counters and the work
-// counters in DevCtl (everything before `overflow`, which stays sticky until the host reads it).
+// test, so earlier draws win ties like in the reference. numVec == 0: the keys already hold the seeds (the
+// last resolve pass left them behind, k_resolve kReseed), only the state reset is needed — and not even that
+// when the resolve pass did it too (the host then skips this launch).
 __global__ void __launch_bounds__(256)
 k_frame_begin(const uint4* __restrict__ depthLayer, uint32_t clearDepthBits, ulonglong2* __restrict__ keys, uint32_t numVec,
-              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileCursor, uint32_t numTiles, DevCtl* __restrict__ ctl) {
+              uint32_t* __restrict__ tileCount, uint32_t* __restrict__ tileCursor, uint32_t numTiles,
+              uint32_t* __restrict__ superCount, uint32_t* __restrict__ superCursor, DevCtl* __restrict__ ctl) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0; }
-    for (uint32_t i = gid; i < numTiles; i += stride) { tileCount[i] = 0; tileCursor[i] = 0; }
+    reset_draw_state(gid, stride, tileCount, tileCursor, numTiles, superCount, superCursor, ctl);
     for (uint32_t i = gid; i < numVec; i += stride) {
         uint4 d = make_uint4(clearDepthBits, clearDepthBits, clearDepthBits, clearDepthBits);
         if (depthLayer != nullptr) d = depthLayer[i];
@@ -55,10 +70,10 @@ k_keys_unpack(const ulonglong2* __restrict__ keys, uint4* __restrict__ color, ui
         bool allWon = l0 != kKeySeed && l1 != kKeySeed && l2 != kKeySeed && l3 != kKeySeed;
         uint4 c = make_uint4(clearColor, clearColor, clearColor, clearColor);
         if (!clearAll && !allWon) c = color[i];
-        if (l0 != kKeySeed) c.x = kKeyIdBase - l0;
-        if (l1 != kKeySeed) c.y = kKeyIdBase - l1;
-        if (l2 != kKeySeed) c.z = kKeyIdBase - l2;
-        if (l3 != kKeySeed) c.w = kKeyIdBase - l3;
+        if (l0 != kKeySeed) c.x = rank_surface_id(kKeyIdBase - l0);
+        if (l1 != kKeySeed) c.y = rank_surface_id(kKeyIdBase - l1);
+        if (l2 != kKeySeed) c.z = rank_surface_id(kKeyIdBase - l2);
+        if (l3 != kKeySeed) c.w = rank_surface_id(kKeyIdBase - l3);
         color[i] = c;
     }
 }
@@ -114,7 +129,7 @@ struct PeerSync {
     unsigned long long waitValue;
     unsigned long long* signalFlag;       // null: no signal
     unsigned long long signalValue;
-    uint32_t* blockCounter;               // this device's scratch counter, zero between launches
+    uint32_t* blockCounter;               // scratch counter of THIS send (one of a ring per device), zero between uses
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {

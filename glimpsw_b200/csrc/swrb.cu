@@ -6,6 +6,7 @@
 //   -> K5 resolve
 // Every call only enqueues work; nothing here computes pixels on the CPU.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -70,18 +71,24 @@ struct swrb_device {
     TriRecord* alphaTris = nullptr;   // alpha-tested triangles (only allocated for scenes with AlphaCutoff < 255 materials)
     TriRecordW* trisW = nullptr;      // their 1/w
     float4* clipRemap = nullptr;      // ClippedU/ClippedV of clipped alpha-tested pieces (2 float4 per alpha record)
-    uint32_t* bigList = nullptr;      // binned: big triangle indices (capacity triCap)
+    uint32_t* superEntries = nullptr; // binned: per-super-tile lists of wide triangles (capacity superCap)
+    uint64_t superCap = 0;
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
     uint32_t* binEntries = nullptr;
     uint64_t binCap = 0;
     uint64_t reserveTris = 0, reserveBins = 0;
+    uint64_t growTris = 0, growBins = 0;    // capacities the next draw must have at least (doubled after an overflow)
 
-    uint32_t* tileCount = nullptr;    // [numTiles] + offsets [numTiles+1] + cursors [numTiles] + active list [numTiles]
+    uint32_t* tileCount = nullptr;    // [numTiles] + offsets [numTiles+1] + cursors [numTiles] + active list [numTiles] + 3 x 160 super-tile words
     uint32_t* tileOffset = nullptr;
     uint32_t* tileCursor = nullptr;
     uint32_t* activeTiles = nullptr;
+    uint32_t* superCount = nullptr;
+    uint32_t* superOffset = nullptr;
+    uint32_t* superCursor = nullptr;
     uint32_t tileCap = 0;
+    bool workClean = false;           // the draw's transient device state (counters, cursors) is already reset (the last resolve pass did it)
 
     DrawItem* drawItems = nullptr;    // device
     uint32_t drawItemCap = 0;
@@ -112,14 +119,17 @@ struct swrb_device {
     uint64_t launches = 0;
     uint64_t hostTimeNs[SWR_PERF_Count_] = {};
     uint32_t lastTriCount = 0;            // records written by the most recent draw the host has read back
-    swrb_fb* lastFb = nullptr;            // target of the last draw (its lazy state is rolled back if that draw aborted)
-    bool lastFbPendingClear = false;
+    // Framebuffers drawn into since the host last saw the overflow flag clear, each with the clear it had pending before its
+    // first such draw: all of them are rolled back when a draw of that window turns out to have aborted.
+    std::vector<std::pair<swrb_fb*, bool>> drawnSinceCheck;
 
     // Per-vertex {x/w, y/w, 1/w, z/w} of the last batch, written by the mesh kernel for the resolve pass.
     // swrb_resolve may read it only if every surface id in the framebuffer provably comes from that batch
     // and the batch used the one matrix the resolve is handed (see clip_cache_usable).
     uint32_t meshBlocksPerSM = 4;         // persistent grid of the mesh kernel (swrb_device_set_mesh_occupancy)
-    uint32_t* peerCounter = nullptr;      // block counter of k_fb_detile_send (multi-GPU composite exchange)
+    uint32_t* peerCounter = nullptr;      // ring of block counters of k_fb_detile_send (one per in-flight send)
+    uint32_t peerCounterNext = 0;
+    static constexpr uint32_t kPeerCounters = 64;
     float4* clipCache = nullptr;
     uint64_t clipCacheCap = 0;            // in meshlets
     swrb_fb* clipCacheFb = nullptr;       // framebuffer the last batch drew into (null = cache unusable)
@@ -164,18 +174,61 @@ struct swrb_fb {
     uint32_t keysClearColor = 0;
     bool layer0IsColor = false;           // resolve already consumed the keys and wrote colour to layer 0
     uint32_t clearColor = 0, clearDepthBits = 0;
+    bool keysSeeded = false;              // the last resolve pass left the next frame's seeds in `keys` (depth = seedDepthBits)
+    uint32_t seedDepthBits = 0;
+    // GetPixels on a side stream: the copy is ordered after the device stream's work (evReady) and everything that
+    // overwrites the layer it reads is ordered after the copy (evCopied).
+    cudaEvent_t evReady = nullptr, evCopied = nullptr;
+    bool copyPending = false;
 };
 
 // An aborted draw (device work list overflow) never touched the depth / id layers; every kernel after it
 // was predicated off by the sticky device flag. Drop its keys and restore the recorded clear, if any.
 static void rollback_aborted_draw(swrb_device* d) {
     d->clipCacheFb = nullptr;
-    if (!d->lastFb) return;
-    d->lastFb->visInKeys = false;
-    d->lastFb->layer0IsColor = false;
-    d->lastFb->pendingClear = d->lastFbPendingClear;
-    d->lastFb = nullptr;
+    d->workClean = false;
+    for (auto& e : d->drawnSinceCheck) {
+        e.first->visInKeys = false;
+        e.first->layer0IsColor = false;
+        e.first->keysSeeded = false;
+        e.first->pendingClear = e.second;
+    }
+    d->drawnSinceCheck.clear();
 }
+static void note_draw_target(swrb_device* d, swrb_fb* fb, bool pendingClearBefore) {
+    for (auto& e : d->drawnSinceCheck) if (e.first == fb) return;       // keep the state before the FIRST draw of the window
+    d->drawnSinceCheck.emplace_back(fb, pendingClearBefore);
+}
+static void forget_draw_target(swrb_device* d, swrb_fb* fb) {
+    for (size_t i = 0; i < d->drawnSinceCheck.size(); i++)
+        if (d->drawnSinceCheck[i].first == fb) { d->drawnSinceCheck.erase(d->drawnSinceCheck.begin() + i); return; }
+}
+
+// NVTX ranges around the stages (the reference marks them with Tracy zones, Rasterizer.cpp:494,518,599,612).
+// libnvToolsExt is only looked for when SWRB_NVTX is set in the environment; without it a range costs one branch.
+struct nvtx_range {
+    typedef int (*push_fn)(const char*);
+    typedef int (*pop_fn)(void);
+    static void resolve(push_fn& push, pop_fn& pop) {
+        static push_fn s_push = nullptr; static pop_fn s_pop = nullptr; static bool tried = false;
+        if (!tried) {
+            tried = true;
+            if (getenv("SWRB_NVTX")) {
+                void* h = dlopen("libnvToolsExt.so.1", RTLD_NOW | RTLD_GLOBAL);
+                if (!h) h = dlopen("libnvToolsExt.so", RTLD_NOW | RTLD_GLOBAL);
+                if (h) { s_push = (push_fn)dlsym(h, "nvtxRangePushA"); s_pop = (pop_fn)dlsym(h, "nvtxRangePop"); }
+            }
+        }
+        push = s_push; pop = s_pop;
+    }
+    pop_fn popFn = nullptr;
+    explicit nvtx_range(const char* name) {
+        push_fn push; pop_fn pop;
+        resolve(push, pop);
+        if (push && pop) { push(name); popFn = pop; }
+    }
+    ~nvtx_range() { if (popFn) popFn(); }
+};
 
 // ---------------------------------------------------------------------------------------------
 struct StageScope {
@@ -211,16 +264,19 @@ static void rollback_aborted_draw(swrb_device* d);
 static int check_overflow(swrb_device* d) {
     // caller has synchronised the stream
     CU(cudaMemcpy(d->ctlHost, d->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost));
-    d->lastTriCount = d->ctlHost->triCount;
+    d->lastTriCount = d->workClean ? d->ctlHost->lastTriCount : d->ctlHost->triCount;
+    if (!d->ctlHost->overflow) d->drawnSinceCheck.clear();
     if (d->ctlHost->overflow) {
         uint32_t which = d->ctlHost->overflow;
         uint32_t zero = 0;
         cudaMemcpy(&d->ctl->overflow, &zero, 4, cudaMemcpyHostToDevice);
         rollback_aborted_draw(d);
+        if (which == 1) d->growTris = std::max<uint64_t>(d->growTris, 2 * d->triCap);
+        else d->growBins = std::max<uint64_t>(d->growBins, 2 * d->binCap);
         return fail(SWRB_E_BIN_OVERFLOW,
-                    "device work list overflowed (%s); the draw was aborted before touching the framebuffer — "
-                    "call swrb_device_reserve() with larger limits and redraw",
-                    which == 1 ? "triangle records" : which == 2 ? "big-triangle work items" : "tile bin entries");
+                    "device work list overflowed (%s); every draw since the last synchronising call was aborted before touching "
+                    "its framebuffer — redraw: the lists are twice as large now (or call swrb_device_reserve() with your own limits)",
+                    which == 1 ? "triangle records" : which == 2 ? "big-triangle work items" : "tile / super-tile bin entries");
     }
     return SWRB_OK;
 }
@@ -277,7 +333,7 @@ void swrb_device_destroy(swrb_device* d) {
     if (!d) return;
     cudaSetDevice(d->cudaDevice);
     cudaStreamSynchronize(d->stream);
-    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->clipRemap); cudaFree(d->alphaTris); cudaFree(d->bigList);
+    cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->clipRemap); cudaFree(d->alphaTris); cudaFree(d->superEntries);
     cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
@@ -354,6 +410,7 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
                       const swr_light* lights, uint32_t num_lights, swrb_scene** out) {
     if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
     if (num_meshlets && !meshlets) return fail(SWRB_E_INVALID, "meshlets is null");
+    if (num_meshlets >= (1u << 24) - 1u) return fail(SWRB_E_INVALID, "%u meshlets: the visibility key orders at most 2^24 - 2 meshlets per scene", num_meshlets);
     CU(cudaSetDevice(d->cudaDevice));
     CreateGuard<swrb_scene, swrb_scene_destroy> guard{ new swrb_scene() };
     swrb_scene* s = guard.p;
@@ -369,6 +426,10 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
         for (uint32_t i = 0; i < num_materials; i++) {
             if (materials[i].AlphaCutoff < 255) s->hasAlphaTest = true;
             if (materials[i].TextureId >= (int32_t)num_textures) return fail(SWRB_E_INVALID, "material %u references texture %d of %u", i, materials[i].TextureId, num_textures);
+            // FS_EncodeSurfaceId<true> samples Material::Texture unconditionally (Shading.cpp:319-326): an alpha-tested material
+            // without a texture is a null dereference upstream, an error here
+            if (materials[i].AlphaCutoff < 255 && materials[i].TextureId < 0)
+                return fail(SWRB_E_INVALID, "material %u is alpha-tested (AlphaCutoff %u < 255) but has no texture", i, materials[i].AlphaCutoff);
         }
         CU(cudaMalloc(&s->materials, num_materials * sizeof(swr_material)));
         CU(cudaMemcpyAsync(s->materials, materials, num_materials * sizeof(swr_material), cudaMemcpyHostToDevice, d->stream));
@@ -408,6 +469,23 @@ int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint3
     if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
     CU(cudaSetDevice(s->dev->cudaDevice));
     CU(cudaMemcpyAsync(s->meshlets + first, meshlets, (size_t)count * sizeof(swr_meshlet), cudaMemcpyHostToDevice, s->dev->stream));
+    if (count) {
+        if (s->attrDirtyLo >= s->attrDirtyHi) { s->attrDirtyLo = first; s->attrDirtyHi = first + count; }
+        else { s->attrDirtyLo = std::min(s->attrDirtyLo, first); s->attrDirtyHi = std::max(s->attrDirtyHi, first + count); }
+        if (s->dev->clipCacheMeshlets == s->meshlets) s->dev->clipCacheFb = nullptr;   // cached vertices belong to the old positions
+    }
+    return SWRB_OK;
+}
+
+int swrb_scene_meshlets_device(swrb_scene* s, void** out) {
+    if (!s || !out) return fail(SWRB_E_INVALID, "null argument");
+    *out = s->meshlets;
+    return SWRB_OK;
+}
+
+int swrb_scene_touch(swrb_scene* s, uint32_t first, uint32_t count) {
+    if (!s) return fail(SWRB_E_INVALID, "scene is null");
+    if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
     if (count) {
         if (s->attrDirtyLo >= s->attrDirtyHi) { s->attrDirtyLo = first; s->attrDirtyHi = first + count; }
         else { s->attrDirtyLo = std::min(s->attrDirtyLo, first); s->attrDirtyHi = std::max(s->attrDirtyHi, first + count); }
@@ -463,6 +541,8 @@ int swrb_fb_create(swrb_device* d, uint32_t width, uint32_t height, uint32_t num
     fb->layerStride = (width * height + 63u) & ~63u;                      // Rasterizer.h:69
     CU(cudaMalloc(&fb->data, (size_t)fb->layerStride * num_layers * 4 + 256));
     CU(cudaMemsetAsync(fb->data, 0, (size_t)fb->layerStride * num_layers * 4, d->stream));
+    CU(cudaEventCreateWithFlags(&fb->evReady, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&fb->evCopied, cudaEventDisableTiming));
     *out = guard.release();
     return SWRB_OK;
 }
@@ -471,9 +551,12 @@ void swrb_fb_destroy(swrb_fb* fb) {
     if (!fb) return;
     cudaSetDevice(fb->dev->cudaDevice);
     cudaStreamSynchronize(fb->dev->stream);
-    if (fb->dev->lastFb == fb) fb->dev->lastFb = nullptr;
+    if (fb->copyPending) cudaEventSynchronize(fb->evCopied);      // a GetPixels on a side stream may still be reading the layers
+    forget_draw_target(fb->dev, fb);
     if (fb->dev->clipCacheFb == fb) fb->dev->clipCacheFb = nullptr;
     cudaFree(fb->data); cudaFree(fb->keys);
+    if (fb->evReady) cudaEventDestroy(fb->evReady);
+    if (fb->evCopied) cudaEventDestroy(fb->evCopied);
     delete fb;
 }
 
@@ -484,8 +567,19 @@ int swrb_fb_info(const swrb_fb* fb, swr_fb_info* out) {
     return SWRB_OK;
 }
 
+// A GetPixels / send on a side stream may still be reading a layer: whatever overwrites the layers on the device's
+// stream waits for it first.
+static int fb_wait_readers(swrb_fb* fb) {
+    if (fb->copyPending) {
+        CU(cudaStreamWaitEvent(fb->dev->stream, fb->evCopied, 0));
+        fb->copyPending = false;
+    }
+    return SWRB_OK;
+}
+
 static int fb_clear_layer_now(swrb_fb* fb, uint32_t layerA, uint32_t valueA, int layerB, uint32_t valueB) {
     swrb_device* d = fb->dev;
+    { int rcw = fb_wait_readers(fb); if (rcw) return rcw; }
     uint32_t numVec = fb->width * fb->height / 4;
     StageScope ss(d, SWRB_STAGE_CLEAR);
     k_fb_clear<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
@@ -505,6 +599,7 @@ static int fb_materialize(swrb_fb* fb) {
         if (rc) return rc;
     }
     if (fb->visInKeys) {
+        { int rcw = fb_wait_readers(fb); if (rcw) return rcw; }
         uint32_t numVec = fb->width * fb->height / 4;
         StageScope ss(d, SWRB_STAGE_RASTER);
         k_keys_unpack<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(
@@ -526,6 +621,7 @@ int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth) {
     // (or any other access materialises it first).
     uint32_t bits; memcpy(&bits, &depth, 4);
     if (bits == 0x80000000u) bits = 0;
+    forget_draw_target(fb->dev, fb);      // a clear recorded after an aborted draw must survive that draw's rollback
     fb->pendingClear = true;
     fb->visInKeys = false;
     fb->layer0IsColor = false;
@@ -573,6 +669,22 @@ static int fb_materialize_for_read(swrb_fb* fb, uint32_t layer) {
     return fb_materialize(fb);
 }
 
+// A copy that runs on another stream than the device's: it must see everything the device stream has enqueued for this
+// framebuffer so far (the resolve pass, a key unpack this very call may have added), and later writers of the layers
+// must wait for it (fb_wait_readers).
+static int fb_order_side_stream(swrb_fb* fb, cudaStream_t stream) {
+    if (stream == fb->dev->stream) return SWRB_OK;
+    CU(cudaEventRecord(fb->evReady, fb->dev->stream));
+    CU(cudaStreamWaitEvent(stream, fb->evReady, 0));
+    return SWRB_OK;
+}
+static int fb_side_stream_done(swrb_fb* fb, cudaStream_t stream) {
+    if (stream == fb->dev->stream) return SWRB_OK;
+    CU(cudaEventRecord(fb->evCopied, stream));
+    fb->copyPending = true;
+    return SWRB_OK;
+}
+
 static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, cudaStream_t stream) {
     if (!fb || !dst_device) return fail(SWRB_E_INVALID, "null argument");
     if (layer >= fb->layers) return fail(SWRB_E_INVALID, "layer %u out of range", layer);
@@ -580,6 +692,8 @@ static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, u
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     int rc = fb_materialize_for_read(fb, layer);
+    if (rc) return rc;
+    rc = fb_order_side_stream(fb, stream);
     if (rc) return rc;
     uint32_t numVec = fb->width * fb->height / 4;
     // On the device's own stream the copy is on the critical path: fill the machine. On a caller's side
@@ -590,7 +704,7 @@ static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, u
         reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride);
     d->launches++;
     CU(cudaGetLastError());
-    return SWRB_OK;
+    return fb_side_stream_done(fb, stream);
 }
 
 int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride) {
@@ -612,22 +726,26 @@ int swrb_fb_send_pixels(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t 
     int rc = fb_materialize_for_read(fb, layer);
     if (rc) return rc;
     if (!d->peerCounter) {
-        CU(cudaMalloc(&d->peerCounter, 256));
-        CU(cudaMemsetAsync(d->peerCounter, 0, 256, d->stream));
+        CU(cudaMalloc(&d->peerCounter, swrb_device::kPeerCounters * 4));
+        CU(cudaMemsetAsync(d->peerCounter, 0, swrb_device::kPeerCounters * 4, d->stream));
         CU(cudaStreamSynchronize(d->stream));
     }
     cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d->stream;
+    rc = fb_order_side_stream(fb, stream);
+    if (rc) return rc;
     PeerSync ps;
     ps.waitFlag = reinterpret_cast<const unsigned long long*>(sync->WaitFlag); ps.waitValue = sync->WaitValue;
     ps.signalFlag = reinterpret_cast<unsigned long long*>(sync->SignalFlag); ps.signalValue = sync->SignalValue;
-    ps.blockCounter = d->peerCounter;
+    // every send in flight counts its finished blocks in its own word (sends of one device may run on several streams);
+    // a word is reused 64 sends later, long after its launch has zeroed it again
+    ps.blockCounter = d->peerCounter + (d->peerCounterNext++ % swrb_device::kPeerCounters);
     // beside the render kernels: one block per SM; measured insensitive to the grid size between 32 and 148 blocks
     // (stores over NVLink are posted, a few hundred KB in flight keep the link busy)
     k_fb_detile_send<<<std::max(1u, (uint32_t)d->numSMs), 256, 0, stream>>>(
         reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride, ps);
     d->launches++;
     CU(cudaGetLastError());
-    return SWRB_OK;
+    return fb_side_stream_done(fb, stream);
 }
 
 int swrb_peer_collect(swrb_device* d, void* cuda_stream, const uint64_t* ready_flags, uint32_t n, uint64_t expected,
@@ -865,15 +983,17 @@ int swrb_cull_meshlets_hiz(swrb_scene* s, uint32_t meshlet_offset, uint32_t coun
 }
 
 // ---- draw --------------------------------------------------------------------------------------
+// Work-list capacities. Only triangles too large for the mesh kernel's inline raster (and alpha-tested / clipped ones) become
+// records, so the lists are sized from what draws actually produce, not from meshlets x 128: start at min(worst case, 2 M
+// records) — or what swrb_device_reserve asked for — and, when a draw does overflow (it is aborted on the device and reported
+// as SWRB_E_BIN_OVERFLOW, never truncated), the next draw finds the capacities doubled.
 static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bool alphaTest) {
-    uint64_t needTris = std::max<uint64_t>(std::max<uint64_t>(maxTris, d->reserveTris), 1024);
+    uint64_t needTris = std::max<uint64_t>(std::max<uint64_t>(std::min<uint64_t>(maxTris, 2u << 20), d->reserveTris), 1024);
+    needTris = std::max(needTris, std::min<uint64_t>(d->growTris, std::max<uint64_t>(maxTris, 1024)));
     if (needTris > d->triCap) {
-        needTris = needTris + needTris / 4;
         uint64_t cap = d->triCap;
         int rc = ensure_buffer((void**)&d->tris, &cap, needTris, sizeof(TriRecord));
         if (rc) return rc;
-        if (d->bigList) { CU(cudaFree(d->bigList)); d->bigList = nullptr; }
-        CU(cudaMalloc(&d->bigList, needTris * 4));
         if (d->trisW) { CU(cudaFree(d->trisW)); d->trisW = nullptr; }
         if (d->clipRemap) { CU(cudaFree(d->clipRemap)); d->clipRemap = nullptr; }
         if (d->alphaTris) { CU(cudaFree(d->alphaTris)); d->alphaTris = nullptr; }
@@ -885,12 +1005,17 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
     }
     const bool clipping = !(d->flags & SWRB_FLAG_BINNING) && (d->flags & SWRB_FLAG_CLIPPING);
     if (alphaTest && clipping && !d->clipRemap) CU(cudaMalloc(&d->clipRemap, d->triCap * 2 * sizeof(float4)));
-    uint64_t needBins = std::max<uint64_t>(d->reserveBins, 2 * d->triCap + (1u << 20));
+    uint64_t needBins = std::max<uint64_t>(std::max<uint64_t>(d->reserveBins, d->growBins), 2 * d->triCap + (1u << 20));   // (also the clip list: 2 words per entry)
     if (needBins > d->binCap) {
         int rc = ensure_buffer((void**)&d->binEntries, &d->binCap, needBins, 4);
         if (rc) return rc;
     }
-    uint64_t needBig = std::max<uint64_t>(1u << 20, d->triCap / 2);
+    uint64_t needSuper = std::max<uint64_t>(std::max<uint64_t>(1u << 18, d->triCap), d->growBins / 4);
+    if (needSuper > d->superCap) {
+        int rc = ensure_buffer((void**)&d->superEntries, &d->superCap, needSuper, 4);
+        if (rc) return rc;
+    }
+    uint64_t needBig = std::max<uint64_t>(std::max<uint64_t>(1u << 20, d->triCap / 2), d->growBins / 2);
     if (needBig > d->bigItemCap) {
         int rc = ensure_buffer((void**)&d->bigItems, &d->bigItemCap, needBig, sizeof(BigItem));
         if (rc) return rc;
@@ -900,12 +1025,16 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
     if (numTiles > d->tileCap) {
         if (d->tileCount) CU(cudaFree(d->tileCount));
         d->tileCount = nullptr;
-        CU(cudaMalloc(&d->tileCount, ((size_t)numTiles * 4 + 4) * 4));
+        CU(cudaMalloc(&d->tileCount, ((size_t)numTiles * 4 + 4 + 3 * 160) * 4));
         d->tileCap = numTiles;
+        d->workClean = false;
     }
     d->tileOffset = d->tileCount + d->tileCap;
     d->tileCursor = d->tileOffset + d->tileCap + 1;
     d->activeTiles = d->tileCursor + d->tileCap;
+    d->superCount = d->activeTiles + d->tileCap;
+    d->superOffset = d->superCount + 160;
+    d->superCursor = d->superOffset + 160;
     return SWRB_OK;
 }
 
@@ -925,59 +1054,28 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
     return fp;
 }
 
-static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
-                         const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws,
-                         bool forResolve = true, uint32_t program = SWRB_PROGRAM_VISBUFFER) {
-    swrb_device* d = fb->dev;
-    CU(cudaSetDevice(d->cudaDevice));
-    if (numDraws == 0) return SWRB_OK;
-    if (program > SWRB_PROGRAM_OVERDRAW) return fail(SWRB_E_INVALID, "unknown program %u", program);
-    const bool binned = (d->flags & SWRB_FLAG_BINNING) != 0;
+// What a draw call hands the kernels: the device-resident per-draw items and what the host knows about them.
+struct DrawList {
+    const DrawItem* items;       // device
+    uint32_t numDraws;
+    uint64_t totalWork;          // meshlets over all draws
+    bool uniformMatrix;          // every draw uses matrix M0 (the clip cache may stand in for the resolve pass's transform)
+    const float* M0;
+};
 
-    // ---- per-draw items
-    uint64_t totalWork = 0;
+// Host draws -> DrawItem array (firstWork prefix, planes, cull bitmap pointers).
+static int fill_draw_items(swrb_device* d, uint32_t numMeshletsDev, const swrb_draw_desc* draws, uint32_t numDraws, DrawItem* items,
+                           uint16_t* cullDev, uint64_t* totalWorkOut, bool* uniformOut, cudaStream_t uploadStream) {
+    uint32_t firstWork = 0;
+    size_t cullCursor = 0;
+    bool uniform = true;
     for (uint32_t i = 0; i < numDraws; i++) {
         if ((uint64_t)draws[i].MeshletOffset + draws[i].MeshletCount > numMeshletsDev)
             return fail(SWRB_E_INVALID, "draw %u: meshlet range [%u,+%u) exceeds the scene's %u meshlets", i, draws[i].MeshletOffset, draws[i].MeshletCount, numMeshletsDev);
-        totalWork += draws[i].MeshletCount;
-    }
-    if (totalWork == 0) return SWRB_OK;
-    if (totalWork >= (1ull << 25)) return fail(SWRB_E_INVALID, "too many meshlets in one batch");
-    int rc = ensure_work_buffers(d, fb, totalWork * SWR_MAX_PRIMS, alphaTest);
-    if (rc) return rc;
-
-    if (numDraws > d->drawItemCap) {
-        if (d->drawItems) CU(cudaFree(d->drawItems));
-        d->drawItems = nullptr;
-        CU(cudaMalloc(&d->drawItems, (size_t)numDraws * sizeof(DrawItem)));
-        d->drawItemCap = numDraws;
-    }
-    int slot = d->drawStagingNext;
-    d->drawStagingNext = (slot + 1) % swrb_device::kStagingSlots;
-    if (d->drawStagingCap[slot] < numDraws) {
-        CU(cudaEventSynchronize(d->drawStagingDone[slot]));
-        if (d->drawStaging[slot]) CU(cudaFreeHost(d->drawStaging[slot]));
-        d->drawStaging[slot] = nullptr;
-        CU(cudaMallocHost(&d->drawStaging[slot], (size_t)numDraws * sizeof(DrawItem)));
-        d->drawStagingCap[slot] = numDraws;
-    } else {
-        CU(cudaEventSynchronize(d->drawStagingDone[slot]));
-    }
-    DrawItem* items = d->drawStaging[slot];
-    uint32_t firstWork = 0;
-    size_t cullWords = 0;
-    for (uint32_t i = 0; i < numDraws; i++) if (draws[i].CullBitmapHost) cullWords += (draws[i].MeshletCount + 15) / 16 + 1;
-    if (cullWords > d->cullUploadCap) {
-        if (d->cullUpload) CU(cudaFree(d->cullUpload));
-        d->cullUpload = nullptr;
-        CU(cudaMalloc(&d->cullUpload, cullWords * 2));
-        d->cullUploadCap = (uint32_t)cullWords;
-    }
-    size_t cullCursor = 0;
-    for (uint32_t i = 0; i < numDraws; i++) {
         DrawItem& it = items[i];
         memcpy(it.M, draws[i].ObjectToClip, sizeof(it.M));
         memcpy(it.planes, draws[i].FrustumPlanes, sizeof(it.planes));
+        memcpy(it.objectToWorld, draws[i].ObjectToWorld, sizeof(it.objectToWorld));
         it.meshletOffset = draws[i].MeshletOffset;
         it.count = draws[i].MeshletCount;
         it.firstWork = firstWork;
@@ -985,74 +1083,108 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         it.cullBitmap = nullptr;
         if (draws[i].CullBitmapHost) {
             size_t words = (draws[i].MeshletCount + 15) / 16;
-            CU(cudaMemcpyAsync(d->cullUpload + cullCursor, draws[i].CullBitmapHost, words * 2, cudaMemcpyHostToDevice, d->stream));
-            it.cullBitmap = d->cullUpload + cullCursor;
+            CU(cudaMemcpyAsync(cullDev + cullCursor, draws[i].CullBitmapHost, words * 2, cudaMemcpyHostToDevice, uploadStream));
+            it.cullBitmap = cullDev + cullCursor;
             cullCursor += words + (words & 1);
         } else if (draws[i].UseDeviceCullBitmap) {
             if (!d->cullBitmapDev || d->cullBitmapCap < draws[i].MeshletCount)
                 return fail(SWRB_E_INVALID, "draw %u: UseDeviceCullBitmap without a preceding swrb_cull_meshlets of >= %u meshlets", i, draws[i].MeshletCount);
             it.cullBitmap = d->cullBitmapDev;
         }
+        if (i && memcmp(draws[i].ObjectToClip, draws[0].ObjectToClip, sizeof(it.M)) != 0) uniform = false;
+        if ((uint64_t)firstWork + draws[i].MeshletCount >= (1ull << 25)) return fail(SWRB_E_INVALID, "too many meshlets in one batch");
         firstWork += draws[i].MeshletCount;
     }
-    CU(cudaMemcpyAsync(d->drawItems, items, (size_t)numDraws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
-    CU(cudaEventRecord(d->drawStagingDone[slot], d->stream));
+    *totalWorkOut = firstWork;
+    *uniformOut = uniform;
+    return SWRB_OK;
+}
+
+static size_t cull_words_needed(const swrb_draw_desc* draws, uint32_t numDraws) {
+    size_t cullWords = 0;
+    for (uint32_t i = 0; i < numDraws; i++) if (draws[i].CullBitmapHost) cullWords += (draws[i].MeshletCount + 15) / 16 + 1;
+    return cullWords;
+}
+
+static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid);
+
+static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
+                     const ResolveTexture* texturesDev, bool alphaTest, const DrawList& dl, bool forResolve, uint32_t program) {
+    swrb_device* d = fb->dev;
+    if (program > SWRB_PROGRAM_DEFERRED) return fail(SWRB_E_INVALID, "unknown program %u", program);
+    if (program == SWRB_PROGRAM_DEFERRED && fb->layers < 3) return fail(SWRB_E_INVALID, "DeferredShader writes three layers (Shading.cpp:344-414); the framebuffer has %u", fb->layers);
+    const bool binned = (d->flags & SWRB_FLAG_BINNING) != 0;
+    const uint32_t numDraws = dl.numDraws;
+    const uint64_t totalWork = dl.totalWork;
+    if (totalWork == 0) return SWRB_OK;
+    int rc = ensure_work_buffers(d, fb, totalWork * SWR_MAX_PRIMS, alphaTest);
+    if (rc) return rc;
+    nvtx_range nv("swrb.draw");
 
     FrameParams fp = frame_params(d, fb, binned);
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t numVec = fb->width * fb->height / 4;
     uint32_t* depthLayer = fb->data + fb->layerStride;
+    MeshOut mo;
+    mo.tris = d->tris; mo.alphaTris = d->alphaTris; mo.alphaW = d->trisW; mo.triCapacity = (uint32_t)std::min<uint64_t>(d->triCap, 0xFFFFFFFFu);
+    mo.tileCount = nullptr; mo.superCount = nullptr; mo.clipList = reinterpret_cast<uint2*>(d->binEntries); mo.clipCache = nullptr;
+    const uint32_t meshGrid = grid_for(d, (totalWork + 31) / 32, kMeshWarps, d->meshBlocksPerSM);   // 64 registers -> at most 4 resident blocks per SM
 
-    // ---- OverdrawShader: no depth test, nothing to resolve lazily — straight into the layers
-    if (program == SWRB_PROGRAM_OVERDRAW) {
+    // ---- OverdrawShader / DeferredShader: no lazy vis-buffer — straight into the layers
+    if (program != SWRB_PROGRAM_VISBUFFER) {
         fp.program = program;
         if (!fb->keys) CU(cudaMalloc(&fb->keys, (size_t)fb->width * fb->height * 8));
         rc = fb_materialize(fb);                // layers current (a recorded clear is executed now)
         if (rc) return rc;
+        rc = fb_wait_readers(fb);
+        if (rc) return rc;
         d->clipCacheFb = nullptr;
-        d->lastFb = nullptr;                    // (no lazy state to roll back: an aborted draw skips k_overdraw_finish)
-        {
-            StageScope ss(d, SWRB_STAGE_CLEAR);
-            k_overdraw_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), numVec, d->ctl);
-            d->launches++;
-        }
-        {
-            StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<grid_for(d, totalWork, kMeshWarps, 4), kMeshWarps * 32, 0, d->stream>>>(
-                meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys, d->tris, d->alphaTris, d->trisW,
-                (uint32_t)d->triCap, nullptr, nullptr, reinterpret_cast<uint2*>(d->binEntries), nullptr, d->ctl);
-            d->launches++;
-            if (fp.clipMode == 2u) {
-                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, d->drawItems, fp,
-                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, (uint32_t)d->triCap, d->ctl);
+        d->workClean = false;
+        fb->keysSeeded = false;                 // the key buffer doubles as this program's scratch
+        const uint32_t recGrid = d->numSMs * 8;
+        if (program == SWRB_PROGRAM_OVERDRAW) {
+            {
+                StageScope ss(d, SWRB_STAGE_CLEAR);
+                k_overdraw_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), numVec, d->ctl);
                 d->launches++;
             }
-        }
-        {
-            StageScope ss(d, SWRB_STAGE_RASTER);
-            k_raster_overdraw<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, fp, fb->keys, depthLayer, d->ctl);
-            k_overdraw_finish<<<grid_for(d, (uint64_t)fb->width * fb->height, 256, 8), 256, 0, d->stream>>>(fb->keys, fb->data, fb->width * fb->height, d->ctl);
-            d->launches += 2;
+            {
+                StageScope ss(d, SWRB_STAGE_MESH);
+                k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
+                d->launches++;
+                if (fp.clipMode == 2u) {
+                    k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
+                                                                      d->tris, d->alphaTris, d->trisW, d->clipRemap, mo.triCapacity, d->ctl);
+                    d->launches++;
+                }
+            }
+            {
+                StageScope ss(d, SWRB_STAGE_RASTER);
+                k_raster_overdraw<<<recGrid, 256, 0, d->stream>>>(d->tris, fp, fb->keys, depthLayer, d->ctl);
+                k_overdraw_finish<<<grid_for(d, (uint64_t)fb->width * fb->height, 256, 8), 256, 0, d->stream>>>(fb->keys, fb->data, fb->width * fb->height, d->ctl);
+                d->launches += 2;
+            }
+        } else {
+            rc = draw_deferred(fb, meshletsDev, materialsDev, texturesDev, dl, fp, mo, meshGrid);
+            if (rc) return rc;
         }
         CU(cudaGetLastError());
         return SWRB_OK;
     }
 
     // ---- per-vertex clip cache for the resolve pass (any batch overwrites it, so it always describes the last one)
-    float4* clipCache = nullptr;
     d->clipCacheFb = nullptr;
     if (forResolve && !(d->flags & SWRB_FLAG_NO_RESOLVE_CACHE)) {
         if (numMeshletsDev > d->clipCacheCap) {
             rc = ensure_buffer((void**)&d->clipCache, &d->clipCacheCap, numMeshletsDev, sizeof(float4) * SWR_MAX_VERTICES);
             if (rc) return rc;
         }
-        clipCache = d->clipCache;
+        mo.clipCache = d->clipCache;
         d->clipCacheFb = fb;
         d->clipCacheMeshlets = meshletsDev;
-        memcpy(d->clipCacheM, draws[0].ObjectToClip, sizeof(d->clipCacheM));
-        d->clipCacheUniform = true;
-        for (uint32_t i = 1; i < numDraws; i++)
-            if (memcmp(draws[i].ObjectToClip, d->clipCacheM, sizeof(d->clipCacheM)) != 0) d->clipCacheUniform = false;
+        memcpy(d->clipCacheM, dl.M0, sizeof(d->clipCacheM));
+        d->clipCacheUniform = dl.uniformMatrix;
     }
 
     // ---- key buffer: seeds = the depth every pixel has before this draw (or the pending clear's depth)
@@ -1062,48 +1194,54 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         if (rc) return rc;
     }
     const int clearMode = fb->pendingClear ? 1 : 0;
-    {
+    // the last resolve pass may have left exactly these seeds behind (and reset the work counters)
+    const bool seeded = clearMode && fb->keysSeeded && fb->seedDepthBits == fb->clearDepthBits;
+    if (!seeded || !d->workClean) {
         StageScope ss(d, SWRB_STAGE_CLEAR);
-        k_frame_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(clearMode ? nullptr : reinterpret_cast<const uint4*>(depthLayer), fb->clearDepthBits,
-                                                                         reinterpret_cast<ulonglong2*>(fb->keys), numVec, d->tileCount, d->tileCursor, numTiles, d->ctl);
+        const uint32_t vec = seeded ? 0u : numVec;
+        k_frame_begin<<<seeded ? 8u : grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(clearMode ? nullptr : reinterpret_cast<const uint4*>(depthLayer), fb->clearDepthBits,
+                                                                         reinterpret_cast<ulonglong2*>(fb->keys), vec, d->tileCount, d->tileCursor, numTiles,
+                                                                         d->superCount, d->superCursor, d->ctl);
         d->launches++;
     }
+    d->workClean = false;
+    fb->keysSeeded = false;
 
-    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, d->meshBlocksPerSM);   // 64 registers -> at most 4 resident blocks per SM
     // record consumers are grid-stride loops over a device-side count; size their grids from the last count
     // the host has seen (any grid is correct, a fitting one avoids launching a thousand idle blocks)
     const uint64_t recEstimate = std::min<uint64_t>(d->triCap, std::max<uint64_t>(4096, 4 * (uint64_t)d->lastTriCount));
     const uint32_t scatterGrid = std::max<uint32_t>(grid_for(d, recEstimate, 256, 8), (uint32_t)d->numSMs);
     if (binned) {
+        mo.tileCount = d->tileCount; mo.superCount = d->superCount;
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                           d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, d->tileCount, d->bigList, nullptr, clipCache, d->ctl);
+            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
             d->launches++;
         }
         {
             StageScope ss(d, SWRB_STAGE_BIN);
-            k_bin_scatter<<<scatterGrid, kScatterThreads, (numTiles + 1) * sizeof(uint32_t), d->stream>>>(
-                d->tris, fp, d->tileCount, d->tileOffset, d->tileCursor, d->activeTiles, d->binEntries,
-                (uint32_t)std::min<uint64_t>(d->binCap, 0xFFFFFFFFu), d->ctl);
+            BinBuffers bb;
+            bb.tileCount = d->tileCount; bb.tileOffset = d->tileOffset; bb.tileCursor = d->tileCursor; bb.activeTiles = d->activeTiles;
+            bb.superCount = d->superCount; bb.superOffset = d->superOffset; bb.superCursor = d->superCursor;
+            bb.binEntries = d->binEntries; bb.binCapacity = (uint32_t)std::min<uint64_t>(d->binCap, 0xFFFFFFFFu);
+            bb.superEntries = d->superEntries; bb.superCapacity = (uint32_t)std::min<uint64_t>(d->superCap, 0xFFFFFFFFu);
+            k_bin_scatter<<<scatterGrid, kScatterThreads, (numTiles + 1) * sizeof(uint32_t), d->stream>>>(d->tris, fp, bb, d->ctl);
             d->launches++;
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
             k_tile_raster<<<std::min<uint32_t>(numTiles, (uint32_t)d->numSMs * 4u), kTileThreads, 0, d->stream>>>(
-                d->tris, d->tileOffset, d->activeTiles, d->binEntries, d->bigList, fp, fb->keys, d->ctl);
+                d->tris, d->tileOffset, d->activeTiles, d->binEntries, d->superOffset, d->superEntries, fp, fb->keys, d->ctl);
             d->launches++;
         }
     } else {
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, d->drawItems, numDraws, (uint32_t)totalWork, fp, fb->keys,
-                                                                            d->tris, d->alphaTris, d->trisW, (uint32_t)d->triCap, nullptr, nullptr,
-                                                                            reinterpret_cast<uint2*>(d->binEntries), clipCache, d->ctl);   // (the bin-entry buffer is idle on this path)
+            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);   // (the bin-entry buffer is idle on this path: it holds the clip list)
             d->launches++;
             if (fp.clipMode == 2u) {       // Clipper::ClipTriangles: pieces join the record / alpha lists before they are consumed
-                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, d->drawItems, fp,
-                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, (uint32_t)d->triCap, d->ctl);
+                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
+                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, mo.triCapacity, d->ctl);
                 d->launches++;
             }
         }
@@ -1122,8 +1260,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the
     // resolve pass reads the keys directly. If a work list overflowed, the draw was aborted on the device
     // and the next synchronising call reports SWRB_E_BIN_OVERFLOW and rolls this state back.
-    d->lastFb = fb;
-    d->lastFbPendingClear = fb->pendingClear;
+    note_draw_target(d, fb, fb->pendingClear);
     fb->visInKeys = true;
     fb->keysClearMode = clearMode != 0;
     fb->keysClearColor = fb->clearColor;
@@ -1131,6 +1268,51 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     fb->pendingClear = false;
     CU(cudaGetLastError());
     return SWRB_OK;
+}
+
+static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid) {
+    (void)fb; (void)meshletsDev; (void)materialsDev; (void)texturesDev; (void)dl; (void)fp; (void)mo; (void)meshGrid;
+    return fail(SWRB_E_UNSUPPORTED, "SWRB_PROGRAM_DEFERRED is not built yet");
+}
+
+// Host-described draws: stage the items in pinned memory, upload, draw.
+static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
+                         const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws,
+                         bool forResolve = true, uint32_t program = SWRB_PROGRAM_VISBUFFER) {
+    swrb_device* d = fb->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    if (numDraws == 0) return SWRB_OK;
+    if (numDraws > d->drawItemCap) {
+        if (d->drawItems) CU(cudaFree(d->drawItems));
+        d->drawItems = nullptr;
+        CU(cudaMalloc(&d->drawItems, (size_t)numDraws * sizeof(DrawItem)));
+        d->drawItemCap = numDraws;
+    }
+    int slot = d->drawStagingNext;
+    d->drawStagingNext = (slot + 1) % swrb_device::kStagingSlots;
+    CU(cudaEventSynchronize(d->drawStagingDone[slot]));
+    if (d->drawStagingCap[slot] < numDraws) {
+        if (d->drawStaging[slot]) CU(cudaFreeHost(d->drawStaging[slot]));
+        d->drawStaging[slot] = nullptr;
+        CU(cudaMallocHost(&d->drawStaging[slot], (size_t)numDraws * sizeof(DrawItem)));
+        d->drawStagingCap[slot] = numDraws;
+    }
+    DrawItem* items = d->drawStaging[slot];
+    const size_t cullWords = cull_words_needed(draws, numDraws);
+    if (cullWords > d->cullUploadCap) {
+        if (d->cullUpload) CU(cudaFree(d->cullUpload));
+        d->cullUpload = nullptr;
+        CU(cudaMalloc(&d->cullUpload, cullWords * 2));
+        d->cullUploadCap = (uint32_t)cullWords;
+    }
+    DrawList dl;
+    int rc = fill_draw_items(d, numMeshletsDev, draws, numDraws, items, d->cullUpload, &dl.totalWork, &dl.uniformMatrix, d->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d->drawItems, items, (size_t)numDraws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
+    CU(cudaEventRecord(d->drawStagingDone[slot], d->stream));
+    dl.items = d->drawItems; dl.numDraws = numDraws; dl.M0 = draws[0].ObjectToClip;
+    return draw_list(fb, meshletsDev, numMeshletsDev, materialsDev, texturesDev, alphaTest, dl, forResolve, program);
 }
 
 int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws) {
@@ -1171,9 +1353,87 @@ int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_host, uint3
     return draw_internal(fb, d->hostDrawMeshlets, count, nullptr, nullptr, false, &desc, 1, /*forResolve=*/false);
 }
 
-// ---- resolve -----------------------------------------------------------------------------------
+// ---- batches and frames: the per-frame host work of the reference's loop, done once ---------------------------------
+struct swrb_batch {
+    swrb_device* dev = nullptr;
+    swrb_scene* scene = nullptr;
+    DrawItem* items = nullptr;       // device
+    uint16_t* cullBitmaps = nullptr; // device copies of the host bitmaps the draws named
+    uint32_t numDraws = 0;
+    uint64_t totalWork = 0;
+    bool uniformMatrix = true;
+    float M0[16] = {};
+};
+
+void swrb_batch_destroy(swrb_batch* b) {
+    if (!b) return;
+    if (b->dev) {
+        cudaSetDevice(b->dev->cudaDevice);
+        cudaStreamSynchronize(b->dev->stream);
+    }
+    cudaFree(b->items); cudaFree(b->cullBitmaps);
+    delete b;
+}
+
+int swrb_batch_create(swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, swrb_batch** out) {
+    if (!scene || !draws || !num_draws || !out) return fail(SWRB_E_INVALID, "null argument");
+    swrb_device* d = scene->dev;
+    CU(cudaSetDevice(d->cudaDevice));
+    for (uint32_t i = 0; i < num_draws; i++)
+        if (draws[i].UseDeviceCullBitmap) return fail(SWRB_E_INVALID, "draw %u: a batch cannot capture the transient device cull bitmap (use FrustumPlanes or CullBitmapHost)", i);
+    CreateGuard<swrb_batch, swrb_batch_destroy> guard{ new swrb_batch() };
+    swrb_batch* b = guard.p;
+    b->dev = d; b->scene = scene; b->numDraws = num_draws;
+    std::vector<DrawItem> items(num_draws);
+    const size_t cullWords = cull_words_needed(draws, num_draws);
+    if (cullWords) CU(cudaMalloc(&b->cullBitmaps, cullWords * 2));
+    int rc = fill_draw_items(d, scene->numMeshlets, draws, num_draws, items.data(), b->cullBitmaps, &b->totalWork, &b->uniformMatrix, d->stream);
+    if (rc) return rc;
+    memcpy(b->M0, draws[0].ObjectToClip, sizeof(b->M0));
+    CU(cudaMalloc(&b->items, (size_t)num_draws * sizeof(DrawItem)));
+    CU(cudaMemcpyAsync(b->items, items.data(), (size_t)num_draws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
+    CU(cudaStreamSynchronize(d->stream));     // the host arrays are only borrowed for the call
+    *out = guard.release();
+    return SWRB_OK;
+}
+
+int swrb_draw_prepared(swrb_fb* fb, const swrb_batch* batch, uint32_t program) {
+    if (!fb || !batch) return fail(SWRB_E_INVALID, "null argument");
+    swrb_scene* scene = batch->scene;
+    if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and batch belong to different devices");
+    CU(cudaSetDevice(fb->dev->cudaDevice));
+    DrawList dl;
+    dl.items = batch->items; dl.numDraws = batch->numDraws; dl.totalWork = batch->totalWork; dl.uniformMatrix = batch->uniformMatrix; dl.M0 = batch->M0;
+    return draw_list(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, dl, true, program);
+}
+
 static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u, int debugLayer);
 
+int swrb_frame_submit(swrb_fb* fb, const swrb_frame_desc* f) {
+    if (!fb || !f || !f->Batch) return fail(SWRB_E_INVALID, "null argument");
+    nvtx_range nv("swrb.frame");
+    int rc = swrb_fb_clear(fb, f->ClearColor, f->ClearDepth);                               // Main.cpp:213
+    if (rc) return rc;
+    rc = swrb_draw_prepared(fb, f->Batch, SWRB_PROGRAM_VISBUFFER);                          // :216-240
+    if (rc) return rc;
+    if (f->Uniforms) {
+        rc = resolve_internal(fb, f->Batch->scene, f->Uniforms, SWRB_LAYER_NONE);            // :249
+        if (rc) return rc;
+    }
+    if (f->PixelsDevice) {                                                                  // :270 (GetPixels)
+        const uint32_t stride = f->PixelsStride ? f->PixelsStride : fb->width;
+        if (f->PeerSync) rc = swrb_fb_send_pixels(fb, 0, f->PixelsDevice, stride, f->PixelsStream, f->PeerSync);
+        else rc = swrb_fb_get_pixels_device_on_stream(fb, 0, f->PixelsDevice, stride, f->PixelsStream ? f->PixelsStream : (void*)fb->dev->stream);
+        if (rc) return rc;
+    }
+    if (f->PixelsHost) {
+        rc = swrb_fb_get_pixels_async(fb, 0, f->PixelsHost, f->PixelsStride ? f->PixelsStride : fb->width);
+        if (rc) return rc;
+    }
+    return SWRB_OK;
+}
+
+// ---- resolve -----------------------------------------------------------------------------------
 int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* u) {
     return resolve_internal(fb, scene, u, SWRB_LAYER_NONE);
 }
@@ -1188,6 +1448,8 @@ int swrb_resolve_debug(swrb_fb* fb, swrb_scene* scene, const swrb_shading_unifor
     CU(cudaSetDevice(d->cudaDevice));
     int rc = fb_materialize(fb);
     if (rc) return rc;
+    rc = fb_wait_readers(fb);
+    if (rc) return rc;
     StageScope ss(d, SWRB_STAGE_RESOLVE);
     dim3 grid((fb->width + 31) / 32, (fb->height + 7) / 8);
     k_resolve_debug_ids<<<grid, dim3(32, 8), 0, d->stream>>>(fb->data, fb->data + fb->layerStride, fb->width, fb->height, (int)layer);
@@ -1201,12 +1463,15 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
     if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
+    nvtx_range nv("swrb.resolve");
     const bool fromKeys = fb->visInKeys && !fb->layer0IsColor;
     if (!fromKeys) {
         int rc = fb_materialize(fb);
         if (rc) return rc;
     }
+    { int rc = fb_wait_readers(fb); if (rc) return rc; }     // the pass overwrites layer 0
     ResolveParams rp;
+    memset(&rp, 0, sizeof(rp));
     memcpy(rp.objectToClip, u->ObjectToClip, sizeof(rp.objectToClip));
     memcpy(rp.objectToWorld, u->ObjectToWorld, sizeof(rp.objectToWorld));
     memcpy(rp.invScreenProj, u->InvScreenProj, sizeof(rp.invScreenProj));
@@ -1217,7 +1482,6 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
     rp.pixBiasX = 0.5f * rp.pixScaleX - 1.0f; rp.pixBiasY = 0.5f * rp.pixScaleY - 1.0f;
     rp.meshlets = scene->meshlets; rp.materials = scene->materials; rp.textures = scene->textures;
     rp.lights = scene->lights; rp.numLights = scene->numLights; rp.numMeshlets = scene->numMeshlets;
-    memset(rp.lightsInline, 0, sizeof(rp.lightsInline));
     for (uint32_t i = 0; i < std::min<uint32_t>(kInlineLights, (uint32_t)scene->lightsHost.size()); i++) rp.lightsInline[i] = scene->lightsHost[i];
     rp.color = fb->data; rp.depth = fb->data + fb->layerStride;
     rp.keys = fb->keys; rp.keysClearMode = fb->keysClearMode ? 1u : 0u; rp.clearColor = fb->keysClearColor;
@@ -1249,6 +1513,16 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
         CU(cudaGetLastError());
         return SWRB_OK;
     }
+    // Reading the keys retires them: the pass stores the depth layer (the layers are current afterwards) and leaves the next
+    // frame's seeds — the framebuffer's last clear depth — and, on the binned path's buffers, a reset draw state behind.
+    if (fromKeys) {
+        rp.reseed = 1u; rp.reseedDepthBits = fb->clearDepthBits;
+        rp.depthOut = fb->data + fb->layerStride; rp.keysOut = fb->keys;
+        if (d->tileCount && !d->workClean) {
+            rp.resetTileCount = d->tileCount; rp.resetTileCursor = d->tileCursor; rp.resetNumTiles = d->tileCap;
+            rp.resetSuperCount = d->superCount; rp.resetSuperCursor = d->superCursor;
+        }
+    }
     {
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         // 4 warps = 16 x 8 pixels per block: small blocks pack better beside other contexts' mesh blocks (measured +2 %
@@ -1260,6 +1534,13 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
         else if (fromKeys) { if (sky) k_resolve<true, false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<true, false><<<grid, block, 0, d->stream>>>(rp, d->ctl); }
         else { if (sky) k_resolve<false, false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<false, false><<<grid, block, 0, d->stream>>>(rp, d->ctl); }
         d->launches++;
+    }
+    if (fromKeys) {
+        fb->visInKeys = false;                       // layers 0 (colour) and 1 (depth) are current
+        fb->layer0IsColor = false;
+        fb->keysSeeded = true; fb->seedDepthBits = fb->clearDepthBits;
+        if (rp.resetTileCount) d->workClean = true;
+        if (d->clipCacheFb == fb) d->clipCacheFb = nullptr;
     }
     // Tail of Resolve (Shading.cpp:690-731): point / spot lights inside the frustum become soft discs, in light order.
     for (const swr_light& light : scene->lightsHost) {
@@ -1280,13 +1561,13 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
         if (ld.startX >= ld.endX || ld.startY >= ld.endY) continue;
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         dim3 grid((uint32_t)(((ld.endX + 3) & ~3) - ld.startX + 31) / 32, (uint32_t)(((ld.endY + 3) & ~3) - ld.startY + 7) / 8);
-        k_light_marker<<<grid, dim3(32, 8), 0, d->stream>>>(ld, fb->data, fb->data + fb->layerStride, fromKeys ? fb->keys : nullptr, fb->width, d->ctl);
+        k_light_marker<<<grid, dim3(32, 8), 0, d->stream>>>(ld, fb->data, fb->data + fb->layerStride, nullptr, fb->width, d->ctl);
         d->launches++;
     }
-    if (fromKeys) fb->layer0IsColor = true;      // depth is still only in the keys
     CU(cudaGetLastError());
     return SWRB_OK;
 }
+
 
 // ---- pinned host memory ------------------------------------------------------------------------
 int swrb_alloc_pinned(swrb_device* d, uint64_t bytes, void** out) {
@@ -1381,7 +1662,9 @@ int swrb_get_draw_stats(swrb_device* d, uint32_t out[4]) {
     CU(cudaStreamSynchronize(d->stream));
     int rc = check_overflow(d);
     if (rc) return rc;
-    out[0] = d->ctlHost->triCount; out[1] = d->ctlHost->bigCount; out[2] = d->ctlHost->binTotal; out[3] = 0;
+    const DevCtl& c = *d->ctlHost;      // after a resolve pass the counters of the finished draw live in last*
+    out[0] = d->workClean ? c.lastTriCount : c.triCount; out[1] = d->workClean ? c.lastBigCount : c.bigCount;
+    out[2] = d->workClean ? c.lastBinTotal : c.binTotal + c.superTotal; out[3] = 0;
     return SWRB_OK;
 }
 

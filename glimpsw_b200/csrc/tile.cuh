@@ -10,8 +10,8 @@
 //   * the others are queued in shared memory and rasterized one per warp: a coarse pass evaluates the
 //     tile's 32 8x4-px blocks at once (one block per lane, trivial reject per edge), then the warp
 //     visits each surviving block with one pixel per lane (fine test);
-//   * the frame's "big" triangles (more than kBigTriTileLimit tiles) are tested against the tile by
-//     all threads and join the same queue.
+//   * the wide triangles (more than kBigTriTileLimit tiles) listed for the tile's 256 x 256-px super-tile
+//     are walked after the tile's own list and take the same two routes.
 // Depth resolution is an order-independent max on the keys (CAS on shared memory, almost always
 // skipped by a plain-load pre-check), which reproduces the reference's one-worker order.
 #pragma once
@@ -116,8 +116,8 @@ __device__ __forceinline__ void tile_raster_warp(const TriRecord& t, const Frame
 // depth / surface-id layers lazily (k_keys_unpack) or are consumed directly by the resolve pass.
 __global__ void __launch_bounds__(kTileThreads)
 k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ tileOffset, const uint32_t* __restrict__ activeTiles,
-              const uint32_t* __restrict__ binEntries, const uint32_t* __restrict__ bigList, FrameParams fp,
-              unsigned long long* __restrict__ keysGlobal, DevCtl* __restrict__ ctl) {
+              const uint32_t* __restrict__ binEntries, const uint32_t* __restrict__ superOffset, const uint32_t* __restrict__ superEntries,
+              FrameParams fp, unsigned long long* __restrict__ keysGlobal, DevCtl* __restrict__ ctl) {
     __shared__ __align__(16) unsigned long long keys[kTilePixels];
     __shared__ uint4 wideRecs[kTileThreads][2];     // records of the chunk's triangles that need a whole warp
     __shared__ uint32_t wideCount;
@@ -132,7 +132,9 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
     const uint32_t tx = tile % fp.tilesX, ty = tile / fp.tilesX;
     const int32_t tileX0 = (int32_t)(tx << kTileShift), tileY0 = (int32_t)(ty << kTileShift);
     const uint32_t listBegin = tileOffset[tile], listEnd = tileOffset[tile + 1];
-    const uint32_t numBig = ctl->bigCount;
+    const uint32_t sh = kSuperShift - kTileShift, superX = (fp.tilesX + (1u << sh) - 1u) >> sh;
+    const uint32_t superTile = (ty >> sh) * superX + (tx >> sh);
+    const uint32_t bigBegin = superOffset[superTile], numBig = superOffset[superTile + 1] - bigBegin;
     if (listBegin == listEnd && numBig == 0) continue;    // nothing binned here: the keys are already final
 
     // ---- stage the tile: thread owns 4 consecutive pixels (one row of a 4x4 fragment)
@@ -152,12 +154,12 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
     if (tid == 0) wideCount = 0;
     __syncthreads();
 
-    // ---- triangles: the tile's list, then the frame's big list
+    // ---- triangles: the tile's list, then its super-tile's list of wide triangles
     const uint32_t total = (listEnd - listBegin) + numBig;
     for (uint32_t base = 0; base < total; base += kTileThreads) {
         uint32_t j = base + tid;
         if (j < total) {
-            uint32_t triIdx = j < (listEnd - listBegin) ? binEntries[listBegin + j] : bigList[j - (listEnd - listBegin)];
+            uint32_t triIdx = j < (listEnd - listBegin) ? binEntries[listBegin + j] : superEntries[bigBegin + (j - (listEnd - listBegin))];
             TriRecord t = load_record(tris, triIdx);
             BBox r;
             if (raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) {

@@ -271,10 +271,16 @@ def icosphere(subdivisions: int):
 
 
 def instanced_scene(subdivisions: int = 6, instances: int = 122, width: int = 1920, height: int = 1080,
-                    seed: int = 4) -> SceneData:
+                    seed: int = 4, bake_transforms: bool = False) -> SceneData:
     """BASELINE config C4: noise-displaced icosphere (81,920 triangles at 6 subdivisions) instanced on a
     jittered 3-D lattice with per-instance rigid transforms (122 instances ~ 9.99 M triangles). The camera
-    sits inside the lattice: most meshlets fail the frustum test and about half of the rest face away."""
+    sits inside the lattice: most meshlets fail the frustum test and about half of the rest face away.
+
+    bake_transforms: the instance transforms are applied to the meshlets on the host (positions, normals, tangents,
+    bounds) and every node's model matrix is the identity. Same triangles, same 122 DrawMeshlets calls, but ONE
+    ObjectToClip for the whole frame — which is what ShadingContext::Resolve assumes (it transforms every pixel with the
+    context's current matrix, Shading.cpp:509-511; README.md:30), so the resolved image of the multi-node scene is
+    meaningful and its parity with the oracle well defined."""
     v, t = icosphere(subdivisions)
     disp = (np.sin(v[:, 0] * 9.0) * np.sin(v[:, 1] * 7.0 + 1.0) * np.sin(v[:, 2] * 8.0 + 2.0)) * 0.06
     disp += (np.sin(v[:, 0] * 31.0 + v[:, 1] * 17.0) * 0.015)
@@ -296,10 +302,25 @@ def instanced_scene(subdivisions: int = 6, instances: int = 122, width: int = 19
         centre = (np.array([gx, gy, gz], dtype=np.float64) - (side - 1) / 2.0) * spacing + (r[i, 0:3] - 0.5) * 1.2
         axis = r[i, 3:6] - 0.5 + 1e-3
         model = cam.mat_mul(cam.translate(centre), cam.mat_mul(cam.rotate_axis(axis, r[i, 6] * 2 * math.pi), cam.scale(0.9 + 0.4 * r[i, 7])))
+        if bake_transforms:
+            A = model.astype(np.float64).T                                   # standard 4x4 (model is stored [c, r])
+            part = meshlets[k:k + nb]
+            P = base["Positions"].astype(np.float64)                          # [nb, 3, 64]
+            part["Positions"] = (np.einsum("rc,mcv->mrv", A[:3, :3], P) + A[:3, 3][None, :, None]).astype(f32)
+            # the displacement is radial, so the object-space normal is the normalised position; any unit vector
+            # perpendicular to it serves as tangent
+            nrm = P / np.maximum(np.linalg.norm(P, axis=1, keepdims=True), 1e-20)
+            tan = np.cross(np.broadcast_to(np.array([0.0, 1.0, 0.0]), np.moveaxis(nrm, 1, 2).shape), np.moveaxis(nrm, 1, 2))
+            tan = tan / np.maximum(np.linalg.norm(tan, axis=2, keepdims=True), 1e-9)
+            Rm = A[:3, :3] / np.linalg.norm(A[:3, 0])
+            part["NormalTangents"] = pack_normal_tangent(np.moveaxis(nrm, 1, 2) @ Rm.T, tan @ Rm.T)
+            model = cam.identity()
         nodes.append(DrawNode(k, nb, model))
         k += nb
+    if bake_transforms:
+        set_bounds(meshlets)
     camera = cam.Camera(position=(0.4, 0.3, 1.6), euler=(0.6, 0.15), fov_deg=90.0, aspect=width / height)
-    return SceneData(f"icosphere{subdivisions}x{instances}", meshlets, nodes, camera, width, height)
+    return SceneData(f"icosphere{subdivisions}x{instances}" + ("_baked" if bake_transforms else ""), meshlets, nodes, camera, width, height)
 
 
 def orbit_cameras(scene: SceneData, count: int, seed: int = 5, radius: float = 6.0):

@@ -39,6 +39,7 @@ typedef enum swrb_status {
 typedef struct swrb_device swrb_device;
 typedef struct swrb_scene swrb_scene;
 typedef struct swrb_fb swrb_fb;
+struct swrb_peer_sync;
 
 /* Rasterizer public toggles — Rasterizer.h:206-208 */
 enum {
@@ -65,6 +66,8 @@ typedef struct swrb_draw_desc {
     const uint16_t* CullBitmapHost;/* ShadingContext::MeshletCullBitmap (host, 1 bit/meshlet) or NULL */
     int32_t  UseDeviceCullBitmap;  /* 1: use the bitmap the last swrb_cull_meshlets left on the device */
     float    FrustumPlanes[5][4];  /* only read with SWRB_FLAG_FUSED_FRUSTUM_CULL */
+    float    ObjectToWorld[9];     /* ShadingContext::ObjectToWorldMat (glm::mat3, column-major): only read by
+                                      SWRB_PROGRAM_DEFERRED (FS_EncodeGBuffer rotates the normals with it) */
 } swrb_draw_desc;
 
 /* ShadingContext resolve-pass uniforms — Shading.h:21-33 */
@@ -104,6 +107,12 @@ SWRB_API int swrb_scene_create(swrb_device* dev,
                                const swr_light* lights, uint32_t num_lights,
                                swrb_scene** out);
 SWRB_API int swrb_scene_update_meshlets(swrb_scene* scene, const swr_meshlet* meshlets, uint32_t first, uint32_t count);
+/* The scene's meshlet array in device memory (num_meshlets x 1728 bytes), for callers that fill it on the device — e.g.
+ * each rank of a multi-GPU job uploads 1/N of the scene from the host and the ranks all-gather the rest over NVLink.
+ * After writing, swrb_scene_touch(first, count) tells the library that derived data of that range is stale; the writes
+ * must be ordered before later swrb calls by the caller (events / stream order on the device's stream). */
+SWRB_API int swrb_scene_meshlets_device(swrb_scene* scene, void** device_ptr_out);
+SWRB_API int swrb_scene_touch(swrb_scene* scene, uint32_t first, uint32_t count);
 /* ShadingContext::SkyboxTex (Shading.h:29, Main.cpp:186): an HdrTexture2D = Texture2D<pixfmt::R11G11B10f> in the reference's
  * TiledY8 storage with its mip chain (Texture.h:133-200, :216), octahedron-mapped. With a skybox set, swrb_resolve gives sky
  * pixels SkyboxTex->SampleOctLevel<EnvSampler>(worldPos - ViewPos, 1) (Shading.cpp:676-679) instead of colour 0.
@@ -183,14 +192,43 @@ SWRB_API int swrb_draw_meshlets_host(swrb_fb* fb, const swr_meshlet* meshlets_ho
 /* ShadingContext::Resolve (Shading.cpp:658-689): overwrites layer 0 with RGBA8 colour. */
 SWRB_API int swrb_resolve(swrb_fb* fb, swrb_scene* scene, const swrb_shading_uniforms* uniforms);
 
-/* The shader tables a DrawMeshlets call can be bound to (ShadingContext::VisBufferShader / OverdrawShader,
- * Shading.h:49, Shading.cpp:648-656). DeferredShader is not offered: its fragment program FS_EncodeGBuffer is an
- * empty function at this snapshot of the reference (Shading.cpp:344-346). */
+/* ---- prepared draws and whole frames ---------------------------------------------------------
+ * The reference's frame loop (Main.cpp:213-252, RasterBench.cpp:92-106) rebuilds the per-node uniforms and calls
+ * DrawMeshlets once per glTF node every frame. A swrb_batch is that list of DrawMeshlets calls validated, laid out and
+ * uploaded ONCE (matrices, frustum planes, copies of host cull bitmaps): drawing it again costs no host staging and no
+ * H2D copy. It captures SWRB_FLAG_FUSED_FRUSTUM_CULL as set at creation. Results equal swrb_draw_batch(draws). */
+typedef struct swrb_batch swrb_batch;
+SWRB_API int swrb_batch_create(swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, swrb_batch** out);
+SWRB_API void swrb_batch_destroy(swrb_batch* batch);
+SWRB_API int swrb_draw_prepared(swrb_fb* fb, const swrb_batch* batch, uint32_t program);
+/* One iteration of that loop in ONE call: Framebuffer::Clear -> DrawMeshlets per node (the batch) -> [Resolve] ->
+ * [GetPixels(layer 0)]. Everything is enqueued on the device's stream except the optional GetPixels, which may run on
+ * `PixelsStream` (NULL = the device stream): the library orders it after the resolve pass and orders the next writer of
+ * layer 0 after it, so callers pipeline frames without any event code of their own. With PeerSync the copy is
+ * swrb_fb_send_pixels (destination in another GPU's memory, flow control folded in). */
+typedef struct swrb_frame_desc {
+    uint32_t ClearColor; float ClearDepth;          /* Framebuffer::Clear(color, depth), Main.cpp:213 */
+    const swrb_batch* Batch;                        /* the frame's DrawMeshlets calls */
+    const swrb_shading_uniforms* Uniforms;          /* ShadingContext::Resolve; NULL = vis-buffer only */
+    void* PixelsDevice; uint32_t PixelsStride;      /* GetPixels(0) into device / peer memory; NULL = none; stride 0 = width */
+    void* PixelsStream;                             /* cudaStream_t of that copy, NULL = device stream */
+    const struct swrb_peer_sync* PeerSync;          /* NULL = plain copy */
+    uint32_t* PixelsHost;                           /* GetPixels(0) into (pinned) host memory, async; NULL = none */
+} swrb_frame_desc;
+SWRB_API int swrb_frame_submit(swrb_fb* fb, const swrb_frame_desc* frame);
+
+/* The shader tables a DrawMeshlets call can be bound to (ShadingContext::VisBufferShader / DeferredShader /
+ * OverdrawShader, Shading.h:49, Shading.cpp:648-656; the Playground picks one per frame, Main.cpp:204-209). */
 typedef enum swrb_program {
     SWRB_PROGRAM_VISBUFFER = 0,   /* ShadeMeshlet + FS_EncodeSurfaceId<false/true> */
-    SWRB_PROGRAM_OVERDRAW  = 1    /* ShadeMeshlet + FS_Overdraw (Shading.cpp:333-342) in every fragment slot: layer 0 counts
+    SWRB_PROGRAM_OVERDRAW  = 1,   /* ShadeMeshlet + FS_Overdraw (Shading.cpp:333-342) in every fragment slot: layer 0 counts
                                      covered pixels (high u16) and helper lanes of touched 4x4 fragments (low u16), saturating;
                                      layer 1 keeps max(depth); no depth test */
+    SWRB_PROGRAM_DEFERRED  = 2    /* ShadeMeshlet + FS_EncodeGBuffer (Shading.cpp:344-414) in every fragment slot: depth test,
+                                     alpha test on the sampled base colour, layer 0 = base colour, layer 1 = depth, layer 2 =
+                                     octahedron-packed world normal (2 x 10 bit) + metallic / roughness (2 x 6 bit). Needs a
+                                     framebuffer with >= 3 layers; the per-draw ObjectToWorld is taken as the upper 3x3 of
+                                     swrb_draw_desc.ObjectToWorld. */
 } swrb_program;
 /* Rasterizer::DrawMeshlets(fb, count, {table, &ctx}) with the table chosen by `program` (Main.cpp:204-209, :236-240). */
 SWRB_API int swrb_draw_batch_program(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, uint32_t program);

@@ -28,9 +28,12 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # swrb_draw_desc: u32,u32,float[16],ptr,i32,float[20] -> 8-byte aligned pointer at offset 72
+    # swrb_draw_desc: u32,u32,float[16],ptr,i32,float[20],float[9] -> 8-byte aligned pointer at offset 72
     assert api.DrawDesc.CullBitmapHost.offset == 72
-    assert ctypes.sizeof(api.DrawDesc) == 168
+    assert api.DrawDesc.ObjectToWorld.offset == 164
+    assert ctypes.sizeof(api.DrawDesc) == 200
+    # swrb_frame_desc: u32,f32,ptr,ptr,ptr,u32,(pad),ptr,ptr,ptr
+    assert api.FrameDesc.PixelsStream.offset == 40 and ctypes.sizeof(api.FrameDesc) == 64
     assert ctypes.sizeof(api.ShadingUniforms) == (16 + 16 + 9 + 16 + 3 + 1) * 4
     assert ctypes.sizeof(api.TextureDesc) == 6 * 4 + 16 * 4 + 8
 
