@@ -122,12 +122,16 @@ k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, BinBuffers bb,
     }
     if (overflow) return;
 
-    // ---- pass 3: one thread per triangle record writes its index into every tile list it overlaps
+    // ---- pass 3: scatter. Records are dealt to the warps of the grid round-robin (record i -> warp i mod W), so a few
+    // thousand records keep a thousand warps busy with 3-4 each instead of a hundred with 32 each. A lane takes one record;
+    // single-tile records are appended with one atomic per distinct tile of the warp, multi-tile ones are expanded by the
+    // whole warp, a lane per tile — the cursor atomics return values (slots), so a lane walking 64 tiles alone would be
+    // 64 dependent L2 round trips.
     const uint32_t lane = lane_id();
-    const uint32_t stride = gridDim.x * kScatterThreads;
-    const uint32_t first = (blockIdx.x * kScatterThreads + threadIdx.x) & ~31u;   // warp-uniform trip count
-    for (uint32_t base = first; base < n; base += stride) {
-        uint32_t i = base + lane;
+    const uint32_t warp = (blockIdx.x * kScatterThreads + threadIdx.x) >> 5, numWarps = (gridDim.x * kScatterThreads) >> 5;
+    for (uint32_t slot0 = 0; slot0 * numWarps < n; slot0 += 32) {       // warp-uniform trip count
+        const uint64_t i64 = (uint64_t)(slot0 + lane) * numWarps + warp;
+        const uint32_t i = i64 < 0xFFFFFFFFull ? (uint32_t)i64 : 0xFFFFFFFFu;
         uint32_t tx0 = 0, ty0 = 0, tx1 = 0, ty1 = 0, nTiles = 0;
         if (i < n) {
             uint4 a = __ldg(reinterpret_cast<const uint4*>(tris + i));
@@ -136,9 +140,9 @@ k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, BinBuffers bb,
             nTiles = tile_range(t, fp, tx0, ty0, tx1, ty1);
         }
         // single-tile triangles: one atomic per distinct tile in the warp
-        bool single = nTiles == 1;
-        uint32_t tile = ty0 * fp.tilesX + tx0;
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, single);
+        const bool single = nTiles == 1;
+        const uint32_t tile = ty0 * fp.tilesX + tx0;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, single);
         if (single) {
             uint32_t peers = __match_any_sync(mask, tile);
             uint32_t leader = (uint32_t)__ffs(peers) - 1u;
@@ -146,20 +150,29 @@ k_bin_scatter(const TriRecord* __restrict__ tris, FrameParams fp, BinBuffers bb,
             if (lane == leader) slot = atomicAdd(&tileCursor[tile], (uint32_t)__popc(peers));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ((1u << lane) - 1u));
             binEntries[sOffset[tile] + slot] = i;
-        } else if (nTiles > (uint32_t)kBigTriTileLimit) {
-            for (uint32_t sy = ty0 >> sh; sy <= (ty1 >> sh); sy++)
-                for (uint32_t sx = tx0 >> sh; sx <= (tx1 >> sh); sx++) {
-                    const uint32_t st = sy * superX + sx;
+        }
+        uint32_t multi = __ballot_sync(0xFFFFFFFFu, nTiles > 1);
+        while (multi) {
+            const uint32_t src = (uint32_t)__ffs(multi) - 1u;
+            multi &= multi - 1u;
+            const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), by0 = __shfl_sync(0xFFFFFFFFu, ty0, src);
+            const uint32_t bx1 = __shfl_sync(0xFFFFFFFFu, tx1, src), by1 = __shfl_sync(0xFFFFFFFFu, ty1, src);
+            const uint32_t rec = __shfl_sync(0xFFFFFFFFu, i, src), cnt = __shfl_sync(0xFFFFFFFFu, nTiles, src);
+            if (cnt > (uint32_t)kBigTriTileLimit) {          // wide: one entry per 256-px super-tile
+                const uint32_t sx0 = bx0 >> sh, sy0 = by0 >> sh, sw = (bx1 >> sh) - sx0 + 1, total = sw * ((by1 >> sh) - sy0 + 1);
+                for (uint32_t t = lane; t < total; t += 32) {
+                    const uint32_t st = (sy0 + t / sw) * superX + sx0 + t % sw;
                     const uint32_t slot = atomicAdd(&bb.superCursor[st], 1u);
-                    bb.superEntries[sSuper[st] + slot] = i;
+                    bb.superEntries[sSuper[st] + slot] = rec;
                 }
-        } else if (nTiles > 1) {
-            for (uint32_t ty = ty0; ty <= ty1; ty++)
-                for (uint32_t tx = tx0; tx <= tx1; tx++) {
-                    uint32_t tl = ty * fp.tilesX + tx;
-                    uint32_t slot = atomicAdd(&tileCursor[tl], 1u);
-                    binEntries[sOffset[tl] + slot] = i;
+            } else {
+                const uint32_t w = bx1 - bx0 + 1;
+                for (uint32_t t = lane; t < cnt; t += 32) {
+                    const uint32_t tl = (by0 + t / w) * fp.tilesX + bx0 + t % w;
+                    const uint32_t slot = atomicAdd(&tileCursor[tl], 1u);
+                    binEntries[sOffset[tl] + slot] = rec;
                 }
+            }
         }
     }
 }

@@ -11,10 +11,9 @@
 //   TriangleEdgeVars::Setup      Rasterizer.cpp:296-329
 //   DrawTriangle<> + FS_EncodeSurfaceId<false>   Rasterizer.h:250-328, Shading.cpp:309-331
 //
-// Work distribution: a persistent grid; every warp takes CHUNKS of 32 consecutive work items (one meshlet of one
-// DrawMeshlets call each) from a device-side cursor. Inside a chunk each LANE tests one meshlet (cull bit, bound
-// sphere against the five frustum planes), so a culled meshlet costs one lane-iteration instead of a whole warp
-// iteration; the survivors (a ballot) are then shaded one after another by the whole warp.
+// Work distribution: a persistent grid, two phases in one launch (see k_mesh_setup): a cull phase in which each LANE tests
+// one meshlet (cull bit, bound sphere against the five frustum planes) and the survivors are appended to a global visible
+// list, then a shade phase in which every warp takes one visible meshlet at a time from a device-side cursor.
 //
 // Staging: the 1,216 hot bytes of a surviving meshlet (header + Positions[3][64], Indices[3][128]) are brought into
 // shared memory by two bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) issued by one lane;
@@ -39,7 +38,7 @@
 namespace swrb {
 
 constexpr int kMeshWarps = 8;           // warps (= meshlets in flight) per block
-constexpr int kInlineMaxArea = 256;     // pixel-region size a lane rasterizes itself (else: record + binner)
+constexpr int kInlineMaxArea = 256;     // largest pixel region a lane may rasterize itself (FrameParams::inlineMaxArea <= this; else: record + binner)
 constexpr uint32_t kMeshStageBytes = 1216;
 
 struct __align__(16) MeshStage {        // the hot bytes of one swr_meshlet, as the bulk copies land them
@@ -133,12 +132,29 @@ struct MeshOut {                         // where the kernel leaves what it does
     float4* clipCache;                            // per-vertex {x/w, y/w, 1/w, z/w} for this frame's resolve pass, or null
 };
 
+// Spin until *p >= want (device scope). Used for the one grid-wide hand-over of the kernel (cull phase -> shade phase).
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <bool kBinned>
 // Persistent grid of 1..4 blocks per SM (swrb_device_set_mesh_occupancy): 4 = the whole register file for a lone frame,
 // 1 leaves room for other render contexts' resolve blocks, whose issue-bound warps fill what these latency-bound ones leave idle.
+//
+// Two phases inside the one launch:
+//   A  cull   (only when the batch has cull bitmaps or fused frustum planes): the warps walk the work items 32 at a time,
+//             one LANE per meshlet (cull bit, bound sphere against the five planes — a culled meshlet costs a lane, not a
+//             warp), and append the survivors {meshlet, draw} to a global visible list (ballot + one atomic per warp step);
+//   B  shade  every warp takes ONE visible meshlet at a time from a device-side cursor — a meshlet of large triangles can
+//             cost 10x the average, so anything coarser leaves a tail — and always has the NEXT one's bulk copy in flight.
+// The phases meet at a grid-wide hand-over: a warp that finished its share of A waits until all of A is published
+// (ctl->cullDone). A is a few microseconds and every block of the persistent grid is resident or becomes resident without
+// our help (other kernels never wait for this one), so the wait cannot deadlock.
 __global__ void __launch_bounds__(kMeshWarps * 32, 4)      // 64 registers: up to 4 blocks = 32 warps per SM
 k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
-             const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, FrameParams fp,
+             const DrawItem* __restrict__ draws, uint32_t numDraws, uint32_t totalWork, uint2* __restrict__ visList, FrameParams fp,
              unsigned long long* __restrict__ keys, MeshOut out, DevCtl* __restrict__ ctl) {
     __shared__ MeshWarpSmem smem[kMeshWarps];
     MeshWarpSmem& s = smem[threadIdx.x >> 5];
@@ -151,20 +167,17 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
     }
     __syncwarp();
     uint32_t nProcessed = 0, nRasterized = 0, nClipped = 0;
-    uint32_t slot = 0, parity = 0;       // bit k of `parity`: phase the next wait on stage k expects
-    const uint32_t numChunks = (totalWork + 31u) >> 5;
+    const uint32_t warpGlobal = blockIdx.x * kMeshWarps + (threadIdx.x >> 5), warpsTotal = gridDim.x * kMeshWarps;
+    uint32_t numItems = totalWork;       // visList == null: no culling anywhere in the batch, item i IS work item i
 
-    for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&ctl->workCursor, 1u);
-        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        if (chunk >= numChunks) break;
-
-        // ---- per lane: one work item = (draw, meshlet of that draw); cull bit + frustum test (ShadeMeshlet :282-289, CullMeshlets :803-809)
-        const uint32_t work = chunk * 32u + lane;
-        bool vis = work < totalWork;
-        uint32_t dIdx = 0, meshletId = 0;
-        {
+    if (visList != nullptr) {
+        // ---- phase A: cull. ShadeMeshlet's cull bit (Shading.cpp:282-289) + CullMeshlets' frustum test (:803-809)
+        const uint32_t numChunks = (totalWork + 31u) >> 5;
+        uint32_t myChunks = 0;
+        for (uint32_t chunk = warpGlobal; chunk < numChunks; chunk += warpsTotal, myChunks++) {
+            const uint32_t work = chunk * 32u + lane;
+            bool vis = work < totalWork;
+            uint32_t dIdx = 0, meshletId = 0;
             uint32_t lo = 0, hi = numDraws;                     // warp-uniform: last draw with firstWork <= the chunk's first item
             while (hi - lo > 1) {
                 uint32_t mid = (lo + hi) >> 1;
@@ -191,27 +204,66 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     }
                 }
             }
-        }
-        uint32_t alive = __ballot_sync(0xFFFFFFFFu, vis);
-        if (alive == 0) continue;
-
-        {   // start the copy of the chunk's first survivor
-            const uint32_t first = (uint32_t)__ffs(alive) - 1u;
-            const uint32_t mid0 = __shfl_sync(0xFFFFFFFFu, meshletId, first);
-            if (lane == 0) stage_issue(&s.stage[slot], &s.bar[slot], meshlets + mid0);
-        }
-        while (alive) {
-            const uint32_t src = (uint32_t)__ffs(alive) - 1u;
-            alive &= alive - 1u;
-            const uint32_t curDraw = __shfl_sync(0xFFFFFFFFu, dIdx, src);
-            const uint32_t curMeshlet = __shfl_sync(0xFFFFFFFFu, meshletId, src);
-            if (alive) {     // the next survivor's bytes travel while this one is shaded
-                const uint32_t nxt = (uint32_t)__ffs(alive) - 1u;
-                const uint32_t midN = __shfl_sync(0xFFFFFFFFu, meshletId, nxt);
-                if (lane == 0) stage_issue(&s.stage[slot ^ 1u], &s.bar[slot ^ 1u], meshlets + midN);
+            const uint32_t alive = __ballot_sync(0xFFFFFFFFu, vis);
+            if (alive) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&ctl->visCount, (uint32_t)__popc(alive));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (vis) visList[base + __popc(alive & ((1u << lane) - 1u))] = make_uint2(meshletId, dIdx);
             }
+        }
+        // publish: this warp's entries, then its share of the chunk count; wait until every chunk has been published
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            if (myChunks) atomicAdd(&ctl->cullDone, myChunks);
+            while (ld_acquire_gpu(&ctl->cullDone) < numChunks) __nanosleep(200);
+        }
+        __syncwarp();
+        numItems = ld_acquire_gpu(&ctl->visCount);
+    }
+
+    // ---- phase B: shade. The warps take the visible meshlets in small batches of consecutive items — the first batch is
+    // the warp's own (no atomic), the later ones come from a device-side cursor, so a meshlet of large triangles (10x the
+    // average cost) delays nobody else — and the next item's bytes are always in flight.
+    uint32_t slot = 0, parity = 0;       // bit k of `parity`: phase the next wait on stage k expects
+    const uint32_t batch = min(max(numItems / (warpsTotal * 4u), 1u), 4u);
+    uint32_t itemNext = warpGlobal * batch, itemEnd = min(itemNext + batch, numItems);
+    auto take_item = [&](uint32_t& meshletId, uint32_t& drawIdx) -> bool {       // warp-uniform
+        if (itemNext >= itemEnd) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(&ctl->workCursor, 1u);
+            b = (__shfl_sync(0xFFFFFFFFu, b, 0) + warpsTotal) * batch;
+            if (b >= numItems) return false;
+            itemNext = b; itemEnd = min(b + batch, numItems);
+        }
+        const uint32_t item = itemNext++;
+        if (visList != nullptr) {
+            const uint2 e = __ldcg(visList + item);
+            meshletId = e.x; drawIdx = e.y;
+        } else {
+            uint32_t lo = 0, hi = numDraws;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (draws[mid].firstWork <= item) lo = mid; else hi = mid;
+            }
+            drawIdx = lo;
+            meshletId = draws[lo].meshletOffset + (item - draws[lo].firstWork);
+        }
+        return true;
+    };
+    uint32_t curMeshlet = 0, curDraw = 0, nxtMeshlet = 0, nxtDraw = 0;
+    bool have = take_item(curMeshlet, curDraw);
+    if (have && lane == 0) stage_issue(&s.stage[slot], &s.bar[slot], meshlets + curMeshlet);
+    while (have) {
+        {
+            const bool haveNext = take_item(nxtMeshlet, nxtDraw);
+            if (haveNext && lane == 0) stage_issue(&s.stage[slot ^ 1u], &s.bar[slot ^ 1u], meshlets + nxtMeshlet);   // travels while this one is shaded
             mbar_wait(&s.bar[slot], (parity >> slot) & 1u);
             parity ^= 1u << slot;
+            have = haveNext;
+        }
+        {
             const MeshStage& st = s.stage[slot];
             slot ^= 1u;
             const DrawItem& d = draws[curDraw];
@@ -231,9 +283,14 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
 
                 // ---- transform + per-vertex setup: lane owns vertices lane and lane+32
                 {
-                    float M[16];
+                    float M[16];            // one matrix for the whole batch rides in the kernel parameters (constant bank)
+                    if (fp.uniformMatrix) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) M[i] = d.M[i];
+                        for (int i = 0; i < 16; i++) M[i] = fp.M[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) M[i] = d.M[i];
+                    }
                     const uint32_t vertSlots = min((numVerts + 15u) & ~15u, 64u);       // reference walks 16-wide vectors
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
@@ -302,7 +359,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                                 BBox r;
                                 if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {     // else: counted, touches no pixel
                                     const int32_t w = r.maxX - r.minX, h = r.maxY - r.minY;
-                                    if (fsId == 0 && w * h <= kInlineMaxArea && fp.program == 0u) {
+                                    if (fsId == 0 && (uint32_t)(w * h) <= fp.inlineMaxArea && fp.program == 0u) {
                                         small = true;
                                         ent = make_uint2((uint32_t)r.minX | ((uint32_t)r.minY << 16),
                                                          (uint32_t)(w - 1) | ((uint32_t)(h - 1) << 8) | (prim << 16));
@@ -413,6 +470,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                 }
             }
             __syncwarp();    // every lane is done with this stage and the per-vertex records before either is overwritten
+            curMeshlet = nxtMeshlet; curDraw = nxtDraw;
         }
     }
 

@@ -73,6 +73,9 @@ struct swrb_device {
     float4* clipRemap = nullptr;      // ClippedU/ClippedV of clipped alpha-tested pieces (2 float4 per alpha record)
     uint32_t* superEntries = nullptr; // binned: per-super-tile lists of wide triangles (capacity superCap)
     uint64_t superCap = 0;
+    uint2* visList = nullptr;         // mesh kernel: {meshlet, draw} of the work items that survive culling
+    uint64_t visListCap = 0;
+    uint32_t inlineMaxArea = 128;     // FrameParams::inlineMaxArea (SWRB_INLINE_AREA in the environment overrides, for experiments)
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
     uint32_t* binEntries = nullptr;
@@ -317,6 +320,7 @@ int swrb_device_create(int cuda_device, swrb_device** out) {
     swrb_device* d = guard.p;
     d->cudaDevice = cuda_device;
     CU(cudaDeviceGetAttribute(&d->numSMs, cudaDevAttrMultiProcessorCount, cuda_device));
+    if (const char* e = getenv("SWRB_INLINE_AREA")) d->inlineMaxArea = (uint32_t)std::min(std::max(atoi(e), 1), kInlineMaxArea);
     CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&d->ctl, sizeof(DevCtl)));
     CU(cudaMemset(d->ctl, 0, sizeof(DevCtl)));
@@ -334,7 +338,7 @@ void swrb_device_destroy(swrb_device* d) {
     cudaSetDevice(d->cudaDevice);
     cudaStreamSynchronize(d->stream);
     cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->clipRemap); cudaFree(d->alphaTris); cudaFree(d->superEntries);
-    cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
+    cudaFree(d->visList); cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
     cudaFree(d->detileScratch); cudaFree(d->clipCache); cudaFree(d->peerCounter); cudaFree(d->l2Scratch);
@@ -1041,6 +1045,9 @@ static int ensure_work_buffers(swrb_device* d, swrb_fb* fb, uint64_t maxTris, bo
 static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool binned) {
     FrameParams fp;
     fp.program = SWRB_PROGRAM_VISBUFFER;
+    fp.inlineMaxArea = d->inlineMaxArea;
+    fp.uniformMatrix = 0;
+    memset(fp.M, 0, sizeof(fp.M));
     fp.width = fb->width; fp.height = fb->height;
     fp.halfW = (int32_t)fb->width / 2; fp.halfH = (int32_t)fb->height / 2;          // Rasterizer.cpp:508
     fp.fixX = (float)(fp.halfW * 16); fp.fixY = (float)(fp.halfH * 16);               // :272
@@ -1061,14 +1068,15 @@ struct DrawList {
     uint64_t totalWork;          // meshlets over all draws
     bool uniformMatrix;          // every draw uses matrix M0 (the clip cache may stand in for the resolve pass's transform)
     const float* M0;
+    bool anyCull;                // some draw carries a cull bitmap or fused frustum planes (the mesh kernel builds a visible list)
 };
 
 // Host draws -> DrawItem array (firstWork prefix, planes, cull bitmap pointers).
 static int fill_draw_items(swrb_device* d, uint32_t numMeshletsDev, const swrb_draw_desc* draws, uint32_t numDraws, DrawItem* items,
-                           uint16_t* cullDev, uint64_t* totalWorkOut, bool* uniformOut, cudaStream_t uploadStream) {
+                           uint16_t* cullDev, uint64_t* totalWorkOut, bool* uniformOut, bool* anyCullOut, cudaStream_t uploadStream) {
     uint32_t firstWork = 0;
     size_t cullCursor = 0;
-    bool uniform = true;
+    bool uniform = true, anyCull = false;
     for (uint32_t i = 0; i < numDraws; i++) {
         if ((uint64_t)draws[i].MeshletOffset + draws[i].MeshletCount > numMeshletsDev)
             return fail(SWRB_E_INVALID, "draw %u: meshlet range [%u,+%u) exceeds the scene's %u meshlets", i, draws[i].MeshletOffset, draws[i].MeshletCount, numMeshletsDev);
@@ -1092,11 +1100,13 @@ static int fill_draw_items(swrb_device* d, uint32_t numMeshletsDev, const swrb_d
             it.cullBitmap = d->cullBitmapDev;
         }
         if (i && memcmp(draws[i].ObjectToClip, draws[0].ObjectToClip, sizeof(it.M)) != 0) uniform = false;
+        if (it.cullBitmap != nullptr || it.fusedCull) anyCull = true;
         if ((uint64_t)firstWork + draws[i].MeshletCount >= (1ull << 25)) return fail(SWRB_E_INVALID, "too many meshlets in one batch");
         firstWork += draws[i].MeshletCount;
     }
     *totalWorkOut = firstWork;
     *uniformOut = uniform;
+    *anyCullOut = anyCull;
     return SWRB_OK;
 }
 
@@ -1123,13 +1133,25 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     nvtx_range nv("swrb.draw");
 
     FrameParams fp = frame_params(d, fb, binned);
+    fp.uniformMatrix = dl.uniformMatrix ? 1u : 0u;
+    memcpy(fp.M, dl.M0, sizeof(fp.M));
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t numVec = fb->width * fb->height / 4;
     uint32_t* depthLayer = fb->data + fb->layerStride;
     MeshOut mo;
     mo.tris = d->tris; mo.alphaTris = d->alphaTris; mo.alphaW = d->trisW; mo.triCapacity = (uint32_t)std::min<uint64_t>(d->triCap, 0xFFFFFFFFu);
     mo.tileCount = nullptr; mo.superCount = nullptr; mo.clipList = reinterpret_cast<uint2*>(d->binEntries); mo.clipCache = nullptr;
-    const uint32_t meshGrid = grid_for(d, (totalWork + 31) / 32, kMeshWarps, d->meshBlocksPerSM);   // 64 registers -> at most 4 resident blocks per SM
+    // persistent mesh grid (64 registers -> at most 4 resident blocks per SM). With culling in the batch the kernel first
+    // builds a visible-meshlet list (8 bytes per work item at most).
+    const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, d->meshBlocksPerSM);
+    uint2* visList = nullptr;
+    if (dl.anyCull) {
+        if (totalWork > d->visListCap) {
+            rc = ensure_buffer((void**)&d->visList, &d->visListCap, totalWork + totalWork / 8, sizeof(uint2));
+            if (rc) return rc;
+        }
+        visList = d->visList;
+    }
 
     // ---- OverdrawShader / DeferredShader: no lazy vis-buffer — straight into the layers
     if (program != SWRB_PROGRAM_VISBUFFER) {
@@ -1151,7 +1173,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
             }
             {
                 StageScope ss(d, SWRB_STAGE_MESH);
-                k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
+                k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);
                 d->launches++;
                 if (fp.clipMode == 2u) {
                     k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
@@ -1215,7 +1237,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
         mo.tileCount = d->tileCount; mo.superCount = d->superCount;
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
+            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);
             d->launches++;
         }
         {
@@ -1237,7 +1259,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     } else {
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);   // (the bin-entry buffer is idle on this path: it holds the clip list)
+            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);   // (the bin-entry buffer is idle on this path: it holds the clip list)
             d->launches++;
             if (fp.clipMode == 2u) {       // Clipper::ClipTriangles: pieces join the record / alpha lists before they are consumed
                 k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
@@ -1307,7 +1329,7 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
         d->cullUploadCap = (uint32_t)cullWords;
     }
     DrawList dl;
-    int rc = fill_draw_items(d, numMeshletsDev, draws, numDraws, items, d->cullUpload, &dl.totalWork, &dl.uniformMatrix, d->stream);
+    int rc = fill_draw_items(d, numMeshletsDev, draws, numDraws, items, d->cullUpload, &dl.totalWork, &dl.uniformMatrix, &dl.anyCull, d->stream);
     if (rc) return rc;
     CU(cudaMemcpyAsync(d->drawItems, items, (size_t)numDraws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
     CU(cudaEventRecord(d->drawStagingDone[slot], d->stream));
@@ -1361,7 +1383,7 @@ struct swrb_batch {
     uint16_t* cullBitmaps = nullptr; // device copies of the host bitmaps the draws named
     uint32_t numDraws = 0;
     uint64_t totalWork = 0;
-    bool uniformMatrix = true;
+    bool uniformMatrix = true, anyCull = false;
     float M0[16] = {};
 };
 
@@ -1387,7 +1409,7 @@ int swrb_batch_create(swrb_scene* scene, const swrb_draw_desc* draws, uint32_t n
     std::vector<DrawItem> items(num_draws);
     const size_t cullWords = cull_words_needed(draws, num_draws);
     if (cullWords) CU(cudaMalloc(&b->cullBitmaps, cullWords * 2));
-    int rc = fill_draw_items(d, scene->numMeshlets, draws, num_draws, items.data(), b->cullBitmaps, &b->totalWork, &b->uniformMatrix, d->stream);
+    int rc = fill_draw_items(d, scene->numMeshlets, draws, num_draws, items.data(), b->cullBitmaps, &b->totalWork, &b->uniformMatrix, &b->anyCull, d->stream);
     if (rc) return rc;
     memcpy(b->M0, draws[0].ObjectToClip, sizeof(b->M0));
     CU(cudaMalloc(&b->items, (size_t)num_draws * sizeof(DrawItem)));
@@ -1404,6 +1426,7 @@ int swrb_draw_prepared(swrb_fb* fb, const swrb_batch* batch, uint32_t program) {
     CU(cudaSetDevice(fb->dev->cudaDevice));
     DrawList dl;
     dl.items = batch->items; dl.numDraws = batch->numDraws; dl.totalWork = batch->totalWork; dl.uniformMatrix = batch->uniformMatrix; dl.M0 = batch->M0;
+    dl.anyCull = batch->anyCull;
     return draw_list(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, dl, true, program);
 }
 
