@@ -40,6 +40,7 @@ namespace swrb {
 constexpr int kMeshWarps = 8;           // warps (= meshlets in flight) per block
 constexpr int kInlineMaxArea = 256;     // largest pixel region a lane may rasterize itself (FrameParams::inlineMaxArea <= this; else: record + binner)
 constexpr uint32_t kMeshStageBytes = 1216;
+constexpr float kLargeMeshletPx = 24.0f; // projected bound-sphere radius from which a meshlet is scheduled first (see phase A)
 
 struct __align__(16) MeshStage {        // the hot bytes of one swr_meshlet, as the bulk copies land them
     uint32_t hdr[16];                   // bytes 0..63: bounds, cone, NumVertices/NumTriangles/AlphaCutoff @44, MaterialId @48
@@ -168,7 +169,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
     __syncwarp();
     uint32_t nProcessed = 0, nRasterized = 0, nClipped = 0;
     const uint32_t warpGlobal = blockIdx.x * kMeshWarps + (threadIdx.x >> 5), warpsTotal = gridDim.x * kMeshWarps;
-    uint32_t numItems = totalWork;       // visList == null: no culling anywhere in the batch, item i IS work item i
+    uint32_t numItems = totalWork, numFront = 0;   // visList == null: no culling anywhere in the batch, item i IS work item i
 
     if (visList != nullptr) {
         // ---- phase A: cull. ShadeMeshlet's cull bit (Shading.cpp:282-289) + CullMeshlets' frustum test (:803-809)
@@ -176,7 +177,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
         uint32_t myChunks = 0;
         for (uint32_t chunk = warpGlobal; chunk < numChunks; chunk += warpsTotal, myChunks++) {
             const uint32_t work = chunk * 32u + lane;
-            bool vis = work < totalWork;
+            bool vis = work < totalWork, large = false;
             uint32_t dIdx = 0, meshletId = 0;
             uint32_t lo = 0, hi = numDraws;                     // warp-uniform: last draw with firstWork <= the chunk's first item
             while (hi - lo > 1) {
@@ -193,23 +194,41 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     uint32_t word = d.cullBitmap[meshIdx >> 4];
                     vis = ((word >> (meshIdx & 15u)) & 1u) != 0;
                 }
-                if (vis && d.fusedCull) {
+                float cx = 0.0f, cy = 0.0f, cz = 0.0f, rad = 0.0f;
+                if (vis) {
                     const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(meshlets + meshletId));        // BoundCenter, BoundRadius
-                    float cx = __uint_as_float(hdrA.x), cy = __uint_as_float(hdrA.y), cz = __uint_as_float(hdrA.z);
-                    float rad = __uint_as_float(hdrA.w);
+                    cx = __uint_as_float(hdrA.x); cy = __uint_as_float(hdrA.y); cz = __uint_as_float(hdrA.z);
+                    rad = __uint_as_float(hdrA.w);
+                }
+                if (vis && d.fusedCull) {
 #pragma unroll
                     for (int i = 0; i < 5; i++) {
                         float dist = __fadd_rn(__fmaf_rn(cx, d.planes[i][0], __fmaf_rn(cy, d.planes[i][1], __fmul_rn(cz, d.planes[i][2]))), d.planes[i][3]);
                         vis = vis && (dist > -rad);
                     }
                 }
+                if (vis) {
+                    // Scheduling hint only (no effect on any result): does the bound sphere project to more than ~kLargeMeshletPx
+                    // pixels of radius? Such a meshlet's triangles have pixel regions of tens of pixels and the meshlet costs
+                    // several times the average, so it goes to the front of the list and is started first.
+                    const float* M = fp.uniformMatrix ? fp.M : d.M;
+                    const float cw = M[3] * cx + M[7] * cy + M[11] * cz + M[15];
+                    const float sy = sqrtf(M[1] * M[1] + M[5] * M[5] + M[9] * M[9]);
+                    large = !(rad * sy * (float)fp.halfH <= kLargeMeshletPx * cw);
+                }
             }
             const uint32_t alive = __ballot_sync(0xFFFFFFFFu, vis);
             if (alive) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&ctl->visCount, (uint32_t)__popc(alive));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (vis) visList[base + __popc(alive & ((1u << lane) - 1u))] = make_uint2(meshletId, dIdx);
+                const uint32_t front = __ballot_sync(0xFFFFFFFFu, vis && large), back = alive & ~front;
+                uint32_t baseF = 0, baseB = 0;
+                if (lane == 0) {
+                    if (front) baseF = atomicAdd(&ctl->visCount, (uint32_t)__popc(front));
+                    if (back) baseB = atomicAdd(&ctl->visCountBack, (uint32_t)__popc(back));
+                }
+                baseF = __shfl_sync(0xFFFFFFFFu, baseF, 0);
+                baseB = __shfl_sync(0xFFFFFFFFu, baseB, 0);
+                const uint32_t lt = (1u << lane) - 1u;
+                if (vis) visList[large ? baseF + __popc(front & lt) : totalWork - 1u - (baseB + __popc(back & lt))] = make_uint2(meshletId, dIdx);
             }
         }
         // publish: this warp's entries, then its share of the chunk count; wait until every chunk has been published
@@ -220,26 +239,31 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             while (ld_acquire_gpu(&ctl->cullDone) < numChunks) __nanosleep(200);
         }
         __syncwarp();
-        numItems = ld_acquire_gpu(&ctl->visCount);
+        numFront = ld_acquire_gpu(&ctl->visCount);
+        numItems = numFront + ld_acquire_gpu(&ctl->visCountBack);
     }
 
-    // ---- phase B: shade. The warps take the visible meshlets in small batches of consecutive items — the first batch is
-    // the warp's own (no atomic), the later ones come from a device-side cursor, so a meshlet of large triangles (10x the
-    // average cost) delays nobody else — and the next item's bytes are always in flight.
+    // ---- phase B: shade. The warps take the visible meshlets in small runs of consecutive items: the first run is the
+    // warp's own (no atomic), the later ones come from a device-side cursor and shrink to single meshlets towards the end of
+    // the list (a meshlet of large triangles costs 10x the average; the list starts with those), and the next item's bytes
+    // are always in flight.
     uint32_t slot = 0, parity = 0;       // bit k of `parity`: phase the next wait on stage k expects
-    const uint32_t batch = min(max(numItems / (warpsTotal * 4u), 1u), 4u);
-    uint32_t itemNext = warpGlobal * batch, itemEnd = min(itemNext + batch, numItems);
+    const uint32_t firstRun = min(max(numItems / (warpsTotal * 4u), 1u), 4u);
+    uint32_t itemNext = warpGlobal * firstRun, itemEnd = min(itemNext + firstRun, numItems), seen = warpsTotal * firstRun;
     auto take_item = [&](uint32_t& meshletId, uint32_t& drawIdx) -> bool {       // warp-uniform
         if (itemNext >= itemEnd) {
+            const uint32_t left = numItems > seen ? numItems - seen : 0u;      // as of this warp's last look at the cursor
+            const uint32_t run = min(max(left / (warpsTotal * 2u), 1u), 4u);
             uint32_t b = 0;
-            if (lane == 0) b = atomicAdd(&ctl->workCursor, 1u);
-            b = (__shfl_sync(0xFFFFFFFFu, b, 0) + warpsTotal) * batch;
+            if (lane == 0) b = atomicAdd(&ctl->workCursor, run);
+            b = __shfl_sync(0xFFFFFFFFu, b, 0) + warpsTotal * firstRun;
+            seen = b + run;
             if (b >= numItems) return false;
-            itemNext = b; itemEnd = min(b + batch, numItems);
+            itemNext = b; itemEnd = min(b + run, numItems);
         }
         const uint32_t item = itemNext++;
         if (visList != nullptr) {
-            const uint2 e = __ldcg(visList + item);
+            const uint2 e = __ldcg(visList + (item < numFront ? item : totalWork - 1u - (item - numFront)));
             meshletId = e.x; drawIdx = e.y;
         } else {
             uint32_t lo = 0, hi = numDraws;

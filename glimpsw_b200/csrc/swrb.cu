@@ -75,7 +75,7 @@ struct swrb_device {
     uint64_t superCap = 0;
     uint2* visList = nullptr;         // mesh kernel: {meshlet, draw} of the work items that survive culling
     uint64_t visListCap = 0;
-    uint32_t inlineMaxArea = 128;     // FrameParams::inlineMaxArea (SWRB_INLINE_AREA in the environment overrides, for experiments)
+    uint32_t inlineMaxArea = 64;      // FrameParams::inlineMaxArea; measured on B200: 32 / 64 / 128 / 256 px give 347 / 354 / 362 / 587 us per C4 view and 83 / 65 / 65 / 65 us per C2 frame (SWRB_INLINE_AREA in the environment overrides, for experiments)
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
     uint32_t* binEntries = nullptr;
