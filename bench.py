@@ -25,7 +25,8 @@ over NVLink, --gather p2p; or an NCCL gather, --gather nccl).
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode binned|direct]
 
 --impl reference: the CPU restatement of the reference (oracle/baseline_mt.cpp, all host threads) renders a bounded sample
-of the same batch on rank 0; the upstream binary cannot be built in this image.
+of the same batch on rank 0. (The reference's own sources build here with g++ only on a scalar stand-in for its Clang vector
+types — oracle/_ref, used to PIN the restatement — which would be an unfairly slow denominator)
 """
 from __future__ import annotations
 
@@ -702,7 +703,7 @@ def run_reference(args):
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": wl.description, "step": f"the whole batch of {num_views} views", "triangles_per_view": wl.scene.num_triangles,
                    "triangles_per_step": wl.scene.num_triangles * num_views, "meshlets": len(wl.scene.meshlets), "draws_per_view": len(wl.scene.nodes),
-                   "note": "CPU restatement of GLimpSW's binned AVX-512 path (oracle/baseline_mt.cpp); the upstream binary needs clang + CPM deps and cannot be built here"},
+                   "note": "CPU restatement of GLimpSW's binned AVX-512 path (oracle/baseline_mt.cpp); bit-identical with the reference's own sources built by oracle/ref_build.py, which only compile on a slow lane-array stand-in for Clang's vector types and are therefore not the timed arm"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -1,8 +1,11 @@
 // baseline_mt.cpp — multithreaded AVX-512 restatement of GLimpSW's binned CPU path, used ONLY as the
 // timed CPU baseline (bench.py cpu_baseline / --impl reference) and cross-checked against oracle.cpp.
 //
-// TEST INFRASTRUCTURE ONLY (see oracle.cpp header); PARITY UNPINNED for the same reason. The upstream
-// binary cannot be built here (clang-only source, CPM-fetched deps), so this is reported as
+// TEST INFRASTRUCTURE ONLY (see oracle.cpp header); pinned through oracle.cpp, which it must equal bit for bit
+// (tests/test_baseline_cpu.py) and which is itself pinned to the reference's own code (tests/test_ref_pin.py).
+// The reference's sources do compile here with g++ (oracle/ref_build.py), but only on a lane-array stand-in for its
+// Clang vector types, which is several times slower than an upstream Clang build would be; timing THAT as "the
+// reference" would flatter the GPU. This file is the faster, fairer denominator and is reported as
 // "restatement of GLimpSW's AVX-512 path", kind "port", never as the upstream binary.
 //
 // What it keeps from the reference (Rasterizer.cpp:493-739, Rasterizer.h:250-328, Shading.cpp:281-331):

@@ -4,10 +4,13 @@
 // this file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs can check and time the reference algorithm on the host.
 //
-// PARITY UNPINNED: the reference ships no tests, golden images or known-answer vectors
-// for this path and cannot be compiled in this image (it needs clang
-// vector extensions, _BitInt and CPM-fetched glm/meshoptimizer/stb; only g++ is present).
-// This file is therefore a line-by-line restatement of the reference SOURCE, each function
+// PARITY PINNED against output of the reference itself: the reference ships no tests, golden
+// images or known-answer vectors for this path, but its own Rasterizer.cpp /
+// Shading.cpp / ImageHelpers.cpp compile with g++ from where they lie under /root/reference
+// (oracle/ref_build.py -> oracle/_ref/libswr_ref.so; SIMD.h and GLM replaced by stand-ins, 26
+// one-line syntax edits), and tests/test_ref_pin.py checks that this restatement and that library
+// produce the same words — vis-buffer, counters, cull bitmaps, resolved colour — on every scene it runs.
+// This file is a line-by-line restatement of the reference SOURCE, each function
 // citing the file:line it follows (paths relative to /root/reference/), in the canonical
 // arithmetic of SURVEY.md Appendix A: IEEE-754 binary32 round-to-nearest-even, an FMA
 // exactly where the source writes simd::fma / simd::mul / simd::dot, separately rounded
@@ -609,7 +612,7 @@ int orc_set_reciprocal_mode(int mode) {
 }
 
 const char* orc_build_info() {
-    return "oracle: scalar canonical restatement; parity unpinned (reference has no golden vectors)"
+    return "oracle: scalar canonical restatement; parity pinned against oracle/_ref (the reference's own sources built with g++, tests/test_ref_pin.py)"
 #if defined(__FMA__)
            "; hw-fma"
 #endif

@@ -1,6 +1,7 @@
 // oracle_hiz.cpp — CPU restatement of the HiZ occlusion-culling row.
 //
-// TEST INFRASTRUCTURE ONLY (see oracle.cpp header); PARITY UNPINNED (no upstream golden data).
+// TEST INFRASTRUCTURE ONLY (see oracle.cpp header); PARITY PINNED: same pyramid texels and cull bitmaps as the
+// reference's own ImageHelpers.cpp / Shading.cpp built by oracle/ref_build.py (tests/test_ref_pin.py).
 //   texutil::DownsampleDepth      ImageHelpers.cpp:150-247   depth layer -> half-res R32f min pyramid (TiledY8)
 //   ProjectSphere                 Shading.cpp:264-279
 //   ShadingContext::CullMeshlets  Shading.cpp:775-869        frustum test + HiZ test against the pyramid

@@ -1,7 +1,7 @@
 // oracle_resolve.cpp — CPU restatement of the vis-buffer resolve pass (ShadingContext::Resolve).
 //
-// TEST INFRASTRUCTURE ONLY (see oracle.cpp header). PARITY UNPINNED: the reference has no golden
-// images. Follows, per 4x4 fragment with 16 lanes like the reference:
+// TEST INFRASTRUCTURE ONLY (see oracle.cpp header). PARITY PINNED: bit-identical colour with the reference's
+// own Shading.cpp built by oracle/ref_build.py (tests/test_ref_pin.py). Follows, per 4x4 fragment with 16 lanes like the reference:
 //   ShadingContext::Resolve            Shading.cpp:658-689   (+ DispatchPass Rasterizer.h:225-242)
 //   ResolveSurface / IntersectTriangle Shading.cpp:472-579 / :417-464
 //   EvalLighting / GetLightAttenuation Shading.cpp:602-645 / :581-600, BRDF helpers :17-33
