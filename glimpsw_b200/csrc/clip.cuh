@@ -47,6 +47,7 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
             cullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
             fsId = (mat.AlphaCutoff < 255 && fp.program == 0u) ? 1u : 0u;
         }
+        if (fp.program == SWRB_PROGRAM_DEFERRED) fsId = 1u;                   // every piece needs 1/w and the barycentric remap (FS_EncodeGBuffer interpolates)
 
         ClipVert verts[16];          // 3 + at most 2 new vertices per plane (Clipper::Vertices, nextIdx <= 64 there)
         uint8_t indices[12], outIndices[12];
@@ -123,7 +124,7 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
                 uint4* dst = reinterpret_cast<uint4*>(alphaTris + slot);
                 dst[0] = recA;
                 dst[1] = make_uint4(__float_as_uint(nz[1]), __float_as_uint(nz[2]), id, 2u);   // aux 2: remap follows
-                *reinterpret_cast<float4*>(alphaW + slot) = make_float4(rw[0], rw[1], rw[2], 0.0f);
+                *reinterpret_cast<float4*>(alphaW + slot) = make_float4(rw[0], rw[1], rw[2], __uint_as_float(ent.x));
                 const ClipVert &p0 = verts[ix[0]], &p1 = verts[ix[1]], &p2 = verts[ix[2]];
                 clipRemap[2 * slot + 0] = make_float4(p0.a[4], __fsub_rn(p1.a[4], p0.a[4]), __fsub_rn(p2.a[4], p0.a[4]), p0.a[5]);   // ClippedU, ClippedV (:462-464)
                 clipRemap[2 * slot + 1] = make_float4(__fsub_rn(p1.a[5], p0.a[5]), __fsub_rn(p2.a[5], p0.a[5]), 0.0f, 0.0f);

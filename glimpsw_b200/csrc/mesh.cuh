@@ -169,20 +169,20 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
     __syncwarp();
     uint32_t nProcessed = 0, nRasterized = 0, nClipped = 0;
     const uint32_t warpGlobal = blockIdx.x * kMeshWarps + (threadIdx.x >> 5), warpsTotal = gridDim.x * kMeshWarps;
-    uint32_t numItems = totalWork, numFront = 0;   // visList == null: no culling anywhere in the batch, item i IS work item i
+    uint32_t numItems = fp.workEnd - fp.workBegin, numFront = 0;   // visList == null: no culling anywhere in the batch, item i IS work item i
 
     if (visList != nullptr) {
         // ---- phase A: cull. ShadeMeshlet's cull bit (Shading.cpp:282-289) + CullMeshlets' frustum test (:803-809)
-        const uint32_t numChunks = (totalWork + 31u) >> 5;
+        const uint32_t numChunks = (fp.workEnd - fp.workBegin + 31u) >> 5;
         uint32_t myChunks = 0;
         for (uint32_t chunk = warpGlobal; chunk < numChunks; chunk += warpsTotal, myChunks++) {
-            const uint32_t work = chunk * 32u + lane;
-            bool vis = work < totalWork, large = false;
+            const uint32_t work = fp.workBegin + chunk * 32u + lane;
+            bool vis = work < fp.workEnd, large = false;
             uint32_t dIdx = 0, meshletId = 0;
             uint32_t lo = 0, hi = numDraws;                     // warp-uniform: last draw with firstWork <= the chunk's first item
             while (hi - lo > 1) {
                 uint32_t mid = (lo + hi) >> 1;
-                if (draws[mid].firstWork <= chunk * 32u) lo = mid; else hi = mid;
+                if (draws[mid].firstWork <= fp.workBegin + chunk * 32u) lo = mid; else hi = mid;
             }
             dIdx = lo;
             if (vis) {
@@ -266,13 +266,14 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             const uint2 e = __ldcg(visList + (item < numFront ? item : totalWork - 1u - (item - numFront)));
             meshletId = e.x; drawIdx = e.y;
         } else {
+            const uint32_t work = fp.workBegin + item;
             uint32_t lo = 0, hi = numDraws;
             while (hi - lo > 1) {
                 uint32_t mid = (lo + hi) >> 1;
-                if (draws[mid].firstWork <= item) lo = mid; else hi = mid;
+                if (draws[mid].firstWork <= work) lo = mid; else hi = mid;
             }
             drawIdx = lo;
-            meshletId = draws[lo].meshletOffset + (item - draws[lo].firstWork);
+            meshletId = draws[lo].meshletOffset + (work - draws[lo].firstWork);
         }
         return true;
     };
@@ -303,7 +304,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     cullMode = mat.IsDoubleSided ? SWR_CULL_NONE : SWR_CULL_FRONT_CCW;
                     fsId = mat.AlphaCutoff < 255 ? 1u : 0u;
                 }
-                if (fp.program != 0u) fsId = 0;                                         // one fragment program in every slot
+                if (fp.program != 0u) fsId = fp.program == SWRB_PROGRAM_DEFERRED ? 1u : 0u;   // one fragment program in every slot; FS_EncodeGBuffer needs 1/w per vertex like the alpha program: same record list
 
                 // ---- transform + per-vertex setup: lane owns vertices lane and lane+32
                 {
@@ -450,7 +451,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                         uint4* dst = reinterpret_cast<uint4*>(out.alphaTris + base + j);
                         dst[0] = make_uint4(__float_as_uint(a.w), __float_as_uint(b.w), __float_as_uint(c.w), __float_as_uint(a.z));
                         dst[1] = make_uint4(__float_as_uint(b.z), __float_as_uint(c.z), rankBase | ((prim >> 4) << 5) | (prim & 15u), 1u);
-                        *reinterpret_cast<float4*>(out.alphaW + base + j) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], 0.0f);
+                        *reinterpret_cast<float4*>(out.alphaW + base + j) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], __uint_as_float(curDraw));   // .w: the draw (DeferredShader reads its ObjectToWorld)
                     }
                 } else if (numBig) {
                     uint32_t base = 0;

@@ -29,6 +29,7 @@
 #include "alpha.cuh"
 #include "clip.cuh"
 #include "overdraw.cuh"
+#include "gbuffer.cuh"
 
 using namespace swrb;
 
@@ -163,6 +164,11 @@ struct swrb_scene {
     std::vector<swr_light> lightsHost;    // for the light markers of Resolve (projected on the host)
     uint32_t numLights = 0;
     bool hasAlphaTest = false;
+    // Host copy of "MaterialId == UINT_MAX" per meshlet: DeferredShader treats such meshlets differently (depth only,
+    // Shading.cpp:352-355) and a batch that mixes both kinds is drawn as runs of one kind (draw_deferred).
+    std::vector<uint8_t> materialless;
+    std::vector<int32_t> materialTextureIds;   // host copy of Material::TextureId
+    uint32_t numMaterialless = 0;
 };
 
 struct swrb_fb {
@@ -421,6 +427,8 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     s->dev = d;
     s->numMeshlets = num_meshlets;
     s->attrDirtyLo = 0; s->attrDirtyHi = num_meshlets;
+    s->materialless.resize(num_meshlets);
+    for (uint32_t i = 0; i < num_meshlets; i++) { s->materialless[i] = meshlets[i].MaterialId == SWR_NO_MATERIAL; s->numMaterialless += s->materialless[i]; }
     if (num_meshlets) {
         CU(cudaMalloc(&s->meshlets, (size_t)num_meshlets * sizeof(swr_meshlet)));
         CU(cudaMemcpyAsync(s->meshlets, meshlets, (size_t)num_meshlets * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
@@ -428,6 +436,7 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     s->numMaterials = num_materials;
     if (num_materials) {
         for (uint32_t i = 0; i < num_materials; i++) {
+            s->materialTextureIds.push_back(materials[i].TextureId);
             if (materials[i].AlphaCutoff < 255) s->hasAlphaTest = true;
             if (materials[i].TextureId >= (int32_t)num_textures) return fail(SWRB_E_INVALID, "material %u references texture %d of %u", i, materials[i].TextureId, num_textures);
             // FS_EncodeSurfaceId<true> samples Material::Texture unconditionally (Shading.cpp:319-326): an alpha-tested material
@@ -473,6 +482,11 @@ int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint3
     if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
     CU(cudaSetDevice(s->dev->cudaDevice));
     CU(cudaMemcpyAsync(s->meshlets + first, meshlets, (size_t)count * sizeof(swr_meshlet), cudaMemcpyHostToDevice, s->dev->stream));
+    for (uint32_t i = 0; i < count; i++) {
+        const uint8_t ml = meshlets[i].MaterialId == SWR_NO_MATERIAL;
+        s->numMaterialless += (uint32_t)ml - (uint32_t)s->materialless[first + i];
+        s->materialless[first + i] = ml;
+    }
     if (count) {
         if (s->attrDirtyLo >= s->attrDirtyHi) { s->attrDirtyLo = first; s->attrDirtyHi = first + count; }
         else { s->attrDirtyLo = std::min(s->attrDirtyLo, first); s->attrDirtyHi = std::max(s->attrDirtyHi, first + count); }
@@ -1048,6 +1062,7 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
     fp.inlineMaxArea = d->inlineMaxArea;
     fp.uniformMatrix = 0;
     memset(fp.M, 0, sizeof(fp.M));
+    fp.workBegin = 0; fp.workEnd = 0;
     fp.width = fb->width; fp.height = fb->height;
     fp.halfW = (int32_t)fb->width / 2; fp.halfH = (int32_t)fb->height / 2;          // Rasterizer.cpp:508
     fp.fixX = (float)(fp.halfW * 16); fp.fixY = (float)(fp.halfH * 16);               // :272
@@ -1069,7 +1084,22 @@ struct DrawList {
     bool uniformMatrix;          // every draw uses matrix M0 (the clip cache may stand in for the resolve pass's transform)
     const float* M0;
     bool anyCull;                // some draw carries a cull bitmap or fused frustum planes (the mesh kernel builds a visible list)
+    const uint32_t* runStarts = nullptr;   // DeferredShader on a scene that mixes textured and material-less meshlets: first work
+    uint32_t numRuns = 0;                  // item of every run of one kind (runStarts[0] == 0); null = the batch is one run
 };
+
+// Work-item indices at which a batch switches between textured and material-less meshlets (see gbuffer.cuh).
+static void compute_runs(const swrb_scene* scene, const swrb_draw_desc* draws, uint32_t numDraws, std::vector<uint32_t>& runStarts) {
+    runStarts.clear();
+    if (!scene || scene->numMaterialless == 0 || scene->numMaterialless == scene->numMeshlets) return;
+    uint32_t work = 0;
+    int kind = -1;
+    for (uint32_t i = 0; i < numDraws; i++)
+        for (uint32_t m = 0; m < draws[i].MeshletCount; m++, work++) {
+            const int k = scene->materialless[draws[i].MeshletOffset + m];
+            if (k != kind) { runStarts.push_back(work); kind = k; }
+        }
+}
 
 // Host draws -> DrawItem array (firstWork prefix, planes, cull bitmap pointers).
 static int fill_draw_items(swrb_device* d, uint32_t numMeshletsDev, const swrb_draw_desc* draws, uint32_t numDraws, DrawItem* items,
@@ -1117,7 +1147,7 @@ static size_t cull_words_needed(const swrb_draw_desc* draws, uint32_t numDraws) 
 }
 
 static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
-                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid);
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid, uint2* visList);
 
 static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
                      const ResolveTexture* texturesDev, bool alphaTest, const DrawList& dl, bool forResolve, uint32_t program) {
@@ -1128,13 +1158,14 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     const uint32_t numDraws = dl.numDraws;
     const uint64_t totalWork = dl.totalWork;
     if (totalWork == 0) return SWRB_OK;
-    int rc = ensure_work_buffers(d, fb, totalWork * SWR_MAX_PRIMS, alphaTest);
+    int rc = ensure_work_buffers(d, fb, totalWork * SWR_MAX_PRIMS, alphaTest || program == SWRB_PROGRAM_DEFERRED);   // FS_EncodeGBuffer's records carry 1/w like the alpha program's
     if (rc) return rc;
     nvtx_range nv("swrb.draw");
 
     FrameParams fp = frame_params(d, fb, binned);
     fp.uniformMatrix = dl.uniformMatrix ? 1u : 0u;
     memcpy(fp.M, dl.M0, sizeof(fp.M));
+    fp.workBegin = 0; fp.workEnd = (uint32_t)totalWork;
     const uint32_t numTiles = fp.tilesX * fp.tilesY;
     const uint32_t numVec = fb->width * fb->height / 4;
     uint32_t* depthLayer = fb->data + fb->layerStride;
@@ -1188,7 +1219,8 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
                 d->launches += 2;
             }
         } else {
-            rc = draw_deferred(fb, meshletsDev, materialsDev, texturesDev, dl, fp, mo, meshGrid);
+            mo.alphaTris = d->alphaTris; mo.alphaW = d->trisW;
+            rc = draw_deferred(fb, meshletsDev, materialsDev, texturesDev, dl, fp, mo, meshGrid, visList);
             if (rc) return rc;
         }
         CU(cudaGetLastError());
@@ -1292,16 +1324,53 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     return SWRB_OK;
 }
 
+// ShadingContext::DeferredShader (gbuffer.cuh). The layers are current on entry (draw_list materialized them). Per run of
+// meshlets of one kind: seed the keys with the depth layer, mesh kernel (every surviving triangle -> a record with 1/w
+// and its draw), [clipper], pass 1 (keys), pass 2 (the winners store depth / base colour / packed normal).
 static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
-                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid) {
-    (void)fb; (void)meshletsDev; (void)materialsDev; (void)texturesDev; (void)dl; (void)fp; (void)mo; (void)meshGrid;
-    return fail(SWRB_E_UNSUPPORTED, "SWRB_PROGRAM_DEFERRED is not built yet");
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid, uint2* visList) {
+    swrb_device* d = fb->dev;
+    if (!mo.alphaTris || !mo.alphaW) return fail(SWRB_E_CUDA, "DeferredShader: record lists missing");
+    const uint32_t numVec = fb->width * fb->height / 4;
+    uint32_t* layer0 = fb->data;
+    uint32_t* layer1 = fb->data + fb->layerStride;
+    uint32_t* layer2 = fb->data + 2 * (size_t)fb->layerStride;
+    const uint32_t recGrid = d->numSMs * 8;
+    const uint32_t numRuns = dl.runStarts ? dl.numRuns : 1u;
+    for (uint32_t r = 0; r < numRuns; r++) {
+        fp.workBegin = dl.runStarts ? dl.runStarts[r] : 0u;
+        fp.workEnd = (dl.runStarts && r + 1 < numRuns) ? dl.runStarts[r + 1] : (uint32_t)dl.totalWork;
+        {
+            StageScope ss(d, SWRB_STAGE_CLEAR);
+            k_gbuffer_begin<<<grid_for(d, numVec, 256, 8), 256, 0, d->stream>>>(reinterpret_cast<ulonglong2*>(fb->keys), reinterpret_cast<const uint4*>(layer1), numVec, d->ctl);
+            d->launches++;
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_MESH);
+            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, dl.numDraws, (uint32_t)dl.totalWork, visList, fp, fb->keys, mo, d->ctl);
+            d->launches++;
+            if (fp.clipMode == 2u) {
+                k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
+                                                                  d->tris, d->alphaTris, d->trisW, d->clipRemap, mo.triCapacity, d->ctl);
+                d->launches++;
+            }
+        }
+        {
+            StageScope ss(d, SWRB_STAGE_RASTER);
+            k_raster_gbuffer<false><<<recGrid, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
+                                                                     fb->keys, layer0, layer1, layer2, d->ctl);
+            k_raster_gbuffer<true><<<recGrid, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
+                                                                    fb->keys, layer0, layer1, layer2, d->ctl);
+            d->launches += 2;
+        }
+    }
+    return SWRB_OK;
 }
 
 // Host-described draws: stage the items in pinned memory, upload, draw.
 static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
                          const ResolveTexture* texturesDev, bool alphaTest, const swrb_draw_desc* draws, uint32_t numDraws,
-                         bool forResolve = true, uint32_t program = SWRB_PROGRAM_VISBUFFER) {
+                         bool forResolve = true, uint32_t program = SWRB_PROGRAM_VISBUFFER, const swrb_scene* scene = nullptr) {
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     if (numDraws == 0) return SWRB_OK;
@@ -1334,6 +1403,11 @@ static int draw_internal(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t n
     CU(cudaMemcpyAsync(d->drawItems, items, (size_t)numDraws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
     CU(cudaEventRecord(d->drawStagingDone[slot], d->stream));
     dl.items = d->drawItems; dl.numDraws = numDraws; dl.M0 = draws[0].ObjectToClip;
+    std::vector<uint32_t> runs;
+    if (program == SWRB_PROGRAM_DEFERRED) {
+        compute_runs(scene, draws, numDraws, runs);
+        if (!runs.empty()) { dl.runStarts = runs.data(); dl.numRuns = (uint32_t)runs.size(); }
+    }
     return draw_list(fb, meshletsDev, numMeshletsDev, materialsDev, texturesDev, alphaTest, dl, forResolve, program);
 }
 
@@ -1346,8 +1420,14 @@ int swrb_draw_batch(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws,
 int swrb_draw_batch_program(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draws, uint32_t num_draws, uint32_t program) {
     if (!fb || !scene || (!draws && num_draws)) return fail(SWRB_E_INVALID, "null argument");
     if (fb->dev != scene->dev) return fail(SWRB_E_INVALID, "framebuffer and scene belong to different devices");
+    if (program == SWRB_PROGRAM_DEFERRED) {
+        // FS_EncodeGBuffer samples Material::Texture of every meshlet that has a material (Shading.cpp:364): a null dereference
+        // upstream, an error here
+        for (uint32_t i = 0; i < scene->numMaterials; i++)
+            if (scene->materialTextureIds[i] < 0) return fail(SWRB_E_INVALID, "DeferredShader: material %u has no texture", i);
+    }
     return draw_internal(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, draws, num_draws,
-                         true, program);
+                         true, program, scene);
 }
 
 int swrb_draw_meshlets(swrb_fb* fb, swrb_scene* scene, const swrb_draw_desc* draw) {
@@ -1385,6 +1465,7 @@ struct swrb_batch {
     uint64_t totalWork = 0;
     bool uniformMatrix = true, anyCull = false;
     float M0[16] = {};
+    std::vector<uint32_t> runs;      // compute_runs of the draws (DeferredShader)
 };
 
 void swrb_batch_destroy(swrb_batch* b) {
@@ -1412,6 +1493,7 @@ int swrb_batch_create(swrb_scene* scene, const swrb_draw_desc* draws, uint32_t n
     int rc = fill_draw_items(d, scene->numMeshlets, draws, num_draws, items.data(), b->cullBitmaps, &b->totalWork, &b->uniformMatrix, &b->anyCull, d->stream);
     if (rc) return rc;
     memcpy(b->M0, draws[0].ObjectToClip, sizeof(b->M0));
+    compute_runs(scene, draws, num_draws, b->runs);
     CU(cudaMalloc(&b->items, (size_t)num_draws * sizeof(DrawItem)));
     CU(cudaMemcpyAsync(b->items, items.data(), (size_t)num_draws * sizeof(DrawItem), cudaMemcpyHostToDevice, d->stream));
     CU(cudaStreamSynchronize(d->stream));     // the host arrays are only borrowed for the call
@@ -1427,6 +1509,11 @@ int swrb_draw_prepared(swrb_fb* fb, const swrb_batch* batch, uint32_t program) {
     DrawList dl;
     dl.items = batch->items; dl.numDraws = batch->numDraws; dl.totalWork = batch->totalWork; dl.uniformMatrix = batch->uniformMatrix; dl.M0 = batch->M0;
     dl.anyCull = batch->anyCull;
+    if (program == SWRB_PROGRAM_DEFERRED) {
+        for (uint32_t i = 0; i < scene->numMaterials; i++)
+            if (scene->materialTextureIds[i] < 0) return fail(SWRB_E_INVALID, "DeferredShader: material %u has no texture", i);
+        if (!batch->runs.empty()) { dl.runStarts = batch->runs.data(); dl.numRuns = (uint32_t)batch->runs.size(); }
+    }
     return draw_list(fb, scene->meshlets, scene->numMeshlets, scene->materials, scene->textures, scene->hasAlphaTest, dl, true, program);
 }
 

@@ -118,7 +118,8 @@ public:
     }
 
     // Rasterizer::DrawMeshlets(fb, count, {table, &ctx}) — Rasterizer.cpp:493. `table` names the reference's shader table:
-    // SWRB_PROGRAM_VISBUFFER = ShadingContext::VisBufferShader, SWRB_PROGRAM_OVERDRAW = ShadingContext::OverdrawShader
+    // SWRB_PROGRAM_VISBUFFER = ShadingContext::VisBufferShader, SWRB_PROGRAM_OVERDRAW = ShadingContext::OverdrawShader,
+    // SWRB_PROGRAM_DEFERRED = ShadingContext::DeferredShader (3-layer framebuffer; ctx.ObjectToWorldMat is passed along)
     // (the choice the Playground makes per frame, Main.cpp:204-209).
     template <class Ctx>
     void DrawMeshlets(Framebuffer& fb, uint32_t count, const Ctx& ctx, swrb_program table = SWRB_PROGRAM_VISBUFFER) {
@@ -127,6 +128,7 @@ public:
         d.MeshletOffset = ctx.MeshletOffset;
         d.MeshletCount = count;
         std::memcpy(d.ObjectToClip, &ctx.ObjectToClipMat[0][0], sizeof d.ObjectToClip);
+        std::memcpy(d.ObjectToWorld, &ctx.ObjectToWorldMat[0][0], sizeof d.ObjectToWorld);
         d.CullBitmapHost = reinterpret_cast<const uint16_t*>(ctx.MeshletCullBitmap);
         check(swrb_draw_batch_program(fb.handle(), _scene, &d, 1, table));
     }

@@ -389,6 +389,82 @@ inline void draw_triangle_alpha(uint32_t* color, float* depth, uint32_t width, c
 
 }  // namespace
 
+extern "C" void orc_gbuffer_fragment(const swr_texture_desc* tex, const float* u, const float* v, const float* bary,
+                                     const uint32_t packedNT[3], uint32_t handedness, const float* objectToWorld3,
+                                     uint32_t* baseColor, uint32_t* packedCh2);
+
+namespace {
+
+// Rasterizer::DrawTriangle<FS_EncodeGBuffer, IsClipped> — Rasterizer.h:250-328 + Shading.cpp:344-414 (ShadingContext::
+// DeferredShader, :655): depth test; material-less meshlets store depth only; otherwise base colour -> layer 0 (fragments
+// whose texel is below AlphaCutoff << 24 are discarded — with the default cutoff of 255 that is every texel that is not fully
+// opaque), packed normal / metallic / roughness -> layer 2, depth -> layer 1. `tex` == nullptr: material-less.
+inline void draw_triangle_gbuffer(uint32_t* color, float* depth, uint32_t* ch2, uint32_t width, const TriEdges& e,
+                                  uint32_t bbMin, uint32_t bbMax, const uint32_t packedTC[3], const uint32_t packedNT[3], uint32_t handedness,
+                                  const swr_texture_desc* tex, uint32_t alphaCutoff, const float* objectToWorld3,
+                                  const float* clipU = nullptr, const float* clipV = nullptr) {
+    uint32_t minX = bbMin & 0xFFFF, minY = bbMin >> 16, maxX = bbMax & 0xFFFF, maxY = bbMax >> 16;
+    float uv[3][2];
+    for (int k = 0; k < 3; k++) {
+        uv[k][0] = half_to_float((uint16_t)(packedTC[k] & 0xFFFF));
+        uv[k][1] = half_to_float((uint16_t)(packedTC[k] >> 16));
+    }
+    for (uint32_t y0 = minY; y0 < maxY; y0 += 4) {
+        for (uint32_t x0 = minX; x0 < maxX; x0 += 4) {
+            bool mask[16];
+            bool any = false;
+            float d[16], tu[16], tv[16], bary[16][3];
+            uint32_t off0 = ((x0 & ~3u) << 2) + (y0 & ~3u) * width;
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = x0 + (i & 3), y = y0 + (i >> 2);
+                uint32_t e0 = (uint32_t)e.Edge0 + (uint32_t)e.A12 * x + (uint32_t)e.B12 * y;
+                uint32_t e1 = (uint32_t)e.Edge1 + (uint32_t)e.A20 * x + (uint32_t)e.B20 * y;
+                uint32_t e2 = (uint32_t)e.Edge2 + (uint32_t)e.A01 * x + (uint32_t)e.B01 * y;
+                mask[i] = (int32_t)(e0 | e1 | e2) >= 0;                                // Rasterizer.h:289-290
+                float u = (float)(int32_t)e1, v = (float)(int32_t)e2;
+                d[i] = std::fmaf(u, e.Z10, std::fmaf(v, e.Z20, e.Z0));                 // :296
+                float pw0 = std::fmaf(u + v, -e.W0S, e.W0);                            // :302-310
+                float w = std::fmaf(u, e.W1S, std::fmaf(v, e.W2S, pw0));
+                float rcpW = 1.0f / w;
+                rcpW *= std::fmaf(-w, rcpW, 2.0f);
+                u *= e.W1S * rcpW;
+                v *= e.W2S * rcpW;
+                if (clipU != nullptr) {                                                // :312-318
+                    float cu = std::fmaf(u, clipU[1], std::fmaf(v, clipU[2], clipU[0]));
+                    float cv = std::fmaf(u, clipV[1], std::fmaf(v, clipV[2], clipV[0]));
+                    u = cu, v = cv;
+                }
+                bary[i][0] = 1 - u - v; bary[i][1] = u; bary[i][2] = v;                // :319
+                tu[i] = std::fmaf(uv[0][0], bary[i][0], std::fmaf(uv[1][0], u, uv[2][0] * v));
+                tv[i] = std::fmaf(uv[0][1], bary[i][0], std::fmaf(uv[1][1], u, uv[2][1] * v));
+                any = any || mask[i];
+            }
+            if (!any) continue;                                                        // Rasterizer.h:292
+            any = false;
+            for (int i = 0; i < 16; i++) {                                             // Shading.cpp:346-348
+                mask[i] = mask[i] && (d[i] > depth[off0 + i]);
+                any = any || mask[i];
+            }
+            if (!any) continue;
+            if (tex == nullptr) {                                                      // :352-355
+                for (int i = 0; i < 16; i++) if (mask[i]) depth[off0 + i] = d[i];
+                continue;
+            }
+            uint32_t baseColor[16], packedCh2[16];
+            orc_gbuffer_fragment(tex, tu, tv, &bary[0][0], packedNT, handedness, objectToWorld3, baseColor, packedCh2);
+            for (int i = 0; i < 16; i++) {
+                if (mask[i] && baseColor[i] >= (alphaCutoff << 24)) {                  // :365, :404-406
+                    depth[off0 + i] = d[i];
+                    color[off0 + i] = baseColor[i];
+                    ch2[off0 + i] = packedCh2[i];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 // ShadeMeshlet — Shading.cpp:281-307. cullBitmap may be NULL. `index` is the meshlet index
@@ -471,11 +547,38 @@ void orc_draw_meshlets(uint32_t* color, float* depth, uint32_t width, uint32_t h
                          nullptr, flags, counters);
 }
 
+static void draw_meshlets_impl(uint32_t* color, float* depth, uint32_t* ch2, uint32_t width, uint32_t height,
+                               const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                               const float* objectToClip, const float* objectToWorld3, const uint16_t* cullBitmap,
+                               const swr_material* materials, const swr_texture_desc* textures,
+                               uint32_t flags, uint64_t* counters);
+
 void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_t height,
                           const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
                           const float* objectToClip, const uint16_t* cullBitmap,
                           const swr_material* materials, const swr_texture_desc* textures,
                           uint32_t flags, uint64_t* counters) {
+    draw_meshlets_impl(color, depth, nullptr, width, height, meshlets, meshletOffset, count, objectToClip, nullptr, cullBitmap, materials,
+                       textures, flags & ~16u, counters);
+}
+
+// Rasterizer::DrawMeshlets with ShadingContext::DeferredShader (Shading.cpp:655): FS_EncodeGBuffer in every fragment slot.
+// layers = the three layers of a ShadingContext::NumFbLayers framebuffer (base colour, depth, packed normal/metal/rough);
+// flags bits 0-2 as for orc_draw_meshlets_ex.
+void orc_draw_meshlets_gbuffer(uint32_t* color, float* depth, uint32_t* ch2, uint32_t width, uint32_t height,
+                               const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                               const float* objectToClip, const float* objectToWorld3, const uint16_t* cullBitmap,
+                               const swr_material* materials, const swr_texture_desc* textures,
+                               uint32_t flags, uint64_t* counters) {
+    draw_meshlets_impl(color, depth, ch2, width, height, meshlets, meshletOffset, count, objectToClip, objectToWorld3, cullBitmap, materials,
+                       textures, (flags & 7u) | 16u, counters);
+}
+
+static void draw_meshlets_impl(uint32_t* color, float* depth, uint32_t* ch2, uint32_t width, uint32_t height,
+                               const swr_meshlet* meshlets, uint32_t meshletOffset, uint32_t count,
+                               const float* objectToClip, const float* objectToWorld3, const uint16_t* cullBitmap,
+                               const swr_material* materials, const swr_texture_desc* textures,
+                               uint32_t flags, uint64_t* counters) {
     int halfW = (int)width / 2, halfH = (int)height / 2;                                   // :508
     float bx = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)width : 1.0f;             // :509
     float by = (flags & 1) ? (float)SWR_MAX_RENDER_SIZE / (float)height : 1.0f;
@@ -497,6 +600,14 @@ void orc_draw_meshlets_ex(uint32_t* color, float* depth, uint32_t width, uint32_
             uint32_t surfaceId = (meshletOffset + meshIdx) * SWR_MAX_PRIMS + prim;         // Shading.cpp:328
             if (flags & 8) {                                                               // ShadingContext::OverdrawShader: every slot is FS_Overdraw (Shading.cpp:656)
                 draw_triangle_overdraw(color, depth, width, e, bbMin, bbMax);
+            } else if (flags & 16) {                                                       // ShadingContext::DeferredShader: every slot is FS_EncodeGBuffer (:655)
+                uint32_t i0 = mesh.Indices[0][prim] & 63, i1 = mesh.Indices[1][prim] & 63, i2 = mesh.Indices[2][prim] & 63;
+                uint32_t tc[3] = { src.TexCoords[i0], src.TexCoords[i1], src.TexCoords[i2] };
+                uint32_t nt[3] = { src.NormalTangents[i0], src.NormalTangents[i1], src.NormalTangents[i2] };
+                uint32_t handed = (uint32_t)((src.TangentHandedness >> i0) & 1) << 31;    // Shading.cpp:386
+                const swr_material* m = src.MaterialId != SWR_NO_MATERIAL ? &materials[src.MaterialId] : nullptr;
+                draw_triangle_gbuffer(color, depth, ch2, width, e, bbMin, bbMax, tc, nt, handed, m ? &textures[m->TextureId] : nullptr,
+                                      m ? m->AlphaCutoff : 0, objectToWorld3, clipU, clipV);
             } else if (alpha) {
                 uint32_t tc[3] = { src.TexCoords[mesh.Indices[0][prim] & 63], src.TexCoords[mesh.Indices[1][prim] & 63],
                                    src.TexCoords[mesh.Indices[2][prim] & 63] };

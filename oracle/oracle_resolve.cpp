@@ -375,7 +375,11 @@ void orc_draw_light_markers(uint32_t* color, const float* depth, uint32_t width,
 // Texture2D::SampleImplicitLod<SurfaceSampler>(u, v, layer 0) over one 4x4 fragment (Texture.h:403-410):
 // LOD from 2x2 finite differences inside the fragment (dFdx/dFdy, :260-269), CalcMipLevel(grad) - LerpFracBits
 // (:271-275, :408), fragment-wide filter vote in SampleLevel (:432). Used by the alpha-tested fragment program.
+void orc_sample_implicit_lod_4x4_layer(const swr_texture_desc* tex, const float* u, const float* v, uint32_t layer, uint32_t* out);
 void orc_sample_implicit_lod_4x4(const swr_texture_desc* tex, const float* u, const float* v, uint32_t* out) {
+    orc_sample_implicit_lod_4x4_layer(tex, u, v, 0, out);
+}
+void orc_sample_implicit_lod_4x4_layer(const swr_texture_desc* tex, const float* u, const float* v, uint32_t layer, uint32_t* out) {
     const float scaleLerpU = (float)(tex->Width << 8), scaleLerpV = (float)(tex->Height << 8);
     float su[N], sv[N];
     for (int i = 0; i < N; i++) { su[i] = u[i] * scaleLerpU; sv[i] = v[i] * scaleLerpV; }
@@ -391,7 +395,47 @@ void orc_sample_implicit_lod_4x4(const swr_texture_desc* tex, const float* u, co
         mip[i] = (ilog2(std::fmax(dx, dy)) >> 1) - 8;
         anyMin = anyMin || mip[i] > 0;
     }
-    for (int i = 0; i < N; i++) out[i] = sample_level(*tex, u[i], v[i], 0, mip[i], anyMin);
+    for (int i = 0; i < N; i++) out[i] = sample_level(*tex, u[i], v[i], layer, mip[i], anyMin);
+}
+
+// The shading half of FS_EncodeGBuffer (Shading.cpp:358-402) for one 4x4 fragment of one triangle: base colour = layer 0
+// through SampleImplicitLod; with a second texture layer, the tangent-space normal (Nx Ny from the texture, Z
+// reconstructed) rotated into world space by the interpolated vertex normal / tangent frame, octahedron-mapped and packed
+// 10 + 10 bits beside the top 6 bits of metallic and roughness. `bary` = FragmentVars::Bary per lane.
+void orc_gbuffer_fragment(const swr_texture_desc* tex, const float* u, const float* v, const float* bary /*[16][3]*/,
+                          const uint32_t packedNT[3], uint32_t handedness, const float* objectToWorld3,
+                          uint32_t* baseColor, uint32_t* packedCh2) {
+    orc_sample_implicit_lod_4x4_layer(tex, u, v, 0, baseColor);                             // :364
+    for (int i = 0; i < N; i++) packedCh2[i] = 0;                                         // :368
+    if (tex->NumLayers < 2) return;                                                       // :370
+    uint32_t nmr[N];
+    orc_sample_implicit_lod_4x4_layer(tex, u, v, 1, nmr);                                 // :372
+    V3 n0, n1, n2, t0, t1, t2;
+    unpack_normal_tangent(packedNT[0], n0, t0);                                           // :380-382
+    unpack_normal_tangent(packedNT[1], n1, t1);
+    unpack_normal_tangent(packedNT[2], n2, t2);
+    for (int i = 0; i < N; i++) {
+        const float* b = bary + i * 3;
+        float nx = (float)(nmr[i] & 255) * (1.0f / 127.5f) - 1.0f;                        // :375
+        float ny = (float)((nmr[i] >> 8) & 255) * (1.0f / 127.5f) - 1.0f;
+        float nz = approx_sqrt(1.0f - (nx * nx + ny * ny));                               // :376
+        V3 nl = { bary_lerp(b, n0.x, n1.x, n2.x), bary_lerp(b, n0.y, n1.y, n2.y), bary_lerp(b, n0.z, n1.z, n2.z) };
+        V3 tl = { bary_lerp(b, t0.x, t1.x, t2.x), bary_lerp(b, t0.y, t1.y, t2.y), bary_lerp(b, t0.z, t1.z, t2.z) };
+        V3 normalWS = normalize3(mul_mat3(objectToWorld3, nl));                           // :384
+        V3 tangentWS = normalize3(mul_mat3(objectToWorld3, tl));                          // :385
+        V3 bit = cross3(normalWS, tangentWS);                                             // :388
+        bit = { u2f(f2u(bit.x) ^ handedness), u2f(f2u(bit.y) ^ handedness), u2f(f2u(bit.z) ^ handedness) };   // :389
+        V3 nr = normalize3({ nx * tangentWS.x + ny * bit.x + nz * normalWS.x,             // :392-396
+                             nx * tangentWS.y + ny * bit.y + nz * normalWS.y,
+                             nx * tangentWS.z + ny * bit.z + nz * normalWS.z });
+        float ou, ov;
+        map_octahedron(nr, ou, ov);                                                       // :398
+        uint32_t c = (uint32_t)(ou * 1023.0f + 0.5f);                                     // :399 (conv<uint32_t> truncates)
+        c |= (uint32_t)(ov * 1023.0f + 0.5f) << 10;                                       // :400
+        c |= ((nmr[i] >> 18) & 0x3F) << 20;                                               // :401
+        c |= ((nmr[i] >> 26) & 0x3F) << 26;                                               // :402
+        packedCh2[i] = c;
+    }
 }
 
 // Texture2D::GenerateMip for one layer/level (Texture.h:577-596): 2x2 box filter in float, RNE pack.

@@ -62,13 +62,14 @@ class Framebuffer:
 
 def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, count: int, object_to_clip,
                   cull_bitmap=None, materials=None, guardband: bool = True, counters=None, textures=None,
-                  binned: bool = True, clipping: bool = False, overdraw: bool = False) -> np.ndarray:
+                  binned: bool = True, clipping: bool = False, overdraw: bool = False, deferred: bool = False,
+                  object_to_world3=None) -> np.ndarray:
     """Rasterizer::DrawMeshlets + VisBufferShader (or, with `overdraw`, OverdrawShader = FS_Overdraw, Shading.cpp:333-342,
     :656) on the CPU. Returns the 4 integer perf counters.
 
     With `textures`, alpha-tested materials (AlphaCutoff < 255) run FS_EncodeSurfaceId<true>; without, every
     triangle takes the opaque program. binned=False selects DrawMeshletsST's treatment of non-trivial triangles:
-    clipped and drawn with `clipping`, else dropped without being counted."""
+    clipped and drawn with `clipping`, else dropped without being counted. `deferred`: DeferredShader (G-buffer)."""
     assert meshlets.dtype.itemsize == 1728
     if counters is None:
         counters = np.zeros(4, dtype=np.uint64)
@@ -76,6 +77,13 @@ def draw_meshlets(fb: Framebuffer, meshlets: np.ndarray, meshlet_offset: int, co
     cb = None if cull_bitmap is None else _p(np.ascontiguousarray(cull_bitmap, dtype=np.uint16))
     mats = None if materials is None or len(materials) == 0 else _p(materials)
     descs, keep = (None, None) if not textures else _texture_descs(textures)
+    if deferred:    # ShadingContext::DeferredShader = FS_EncodeGBuffer (Shading.cpp:344-414, :655) into a 3-layer framebuffer
+        assert fb.layers >= 3 and not overdraw
+        o2w = np.ascontiguousarray(np.asarray(object_to_world3 if object_to_world3 is not None else np.eye(3), dtype=np.float32).reshape(9))
+        lib().orc_draw_meshlets_gbuffer(_p(fb.data[0]), _p(fb.data[1]), _p(fb.data[2]), fb.width, fb.height, _p(meshlets),
+                                        C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), _p(o2w), cb, mats, descs,
+                                        C.c_uint32((1 if guardband else 0) | (0 if binned else (2 if clipping else 4))), _p(counters))
+        return counters
     lib().orc_draw_meshlets_ex(_p(fb.data[0]), _p(fb.data[1]), fb.width, fb.height, _p(meshlets),
                                C.c_uint32(meshlet_offset), C.c_uint32(count), _p(m), cb, mats, descs,
                                C.c_uint32((1 if guardband else 0) | (0 if binned else (2 if clipping else 4)) | (8 if overdraw else 0)),

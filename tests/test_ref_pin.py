@@ -220,6 +220,30 @@ def test_overdraw_program_matches(orc, R, mode):
     assert list(oc[:3]) == list(rc[:3]) and int((ofb.data[0] >> 16).max()) >= 2
 
 
+@pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
+def test_deferred_gbuffer_program_matches(orc, R, mode):
+    """DeferredShader = FS_EncodeGBuffer (Shading.cpp:344-414): all three layers — base colour, depth, packed world normal +
+    metallic / roughness — on textured, alpha-tested and clipped geometry and on a scene that mixes in material-less meshlets."""
+    for scene in (scenes.torus_knot_scene(100, 40, 640, 360, tex_size=128), scenes.torus_knot_scene(120, 48, 960, 540, tex_size=64, alpha_material=True),
+                  scenes.patchwork_scene(20, 16, 640, 360), scenes.closeup_alpha_scene()):
+        ofb = orc.Framebuffer(scene.width, scene.height, 3)
+        ofb.clear(0xFF000000, 0.0)
+        ofb.data[2, :] = 0x12345678
+        rfb = ref.Framebuffer(scene.width, scene.height, 3)
+        rfb.data[:] = ofb.data
+        oc, rc = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        for nd in scene.nodes:
+            kw = dict(materials=scene.materials, textures=scene.textures, deferred=True, object_to_world3=np.ascontiguousarray(nd.model[0:3, 0:3]), **mode)
+            orc.draw_meshlets(ofb, scene.meshlets, nd.meshlet_offset, nd.meshlet_count, scene.object_to_clip(nd), counters=oc, **kw)
+            R.draw_meshlets(rfb, scene.meshlets, nd.meshlet_offset, nd.meshlet_count, scene.object_to_clip(nd), counters=rc, **kw)
+        n = scene.width * scene.height
+        for layer in range(3):
+            bad = int((ofb.data[layer, :n] != rfb.data[layer, :n]).sum())
+            assert bad == 0, f"{scene.name}: {bad} words of layer {layer} differ"
+        assert list(oc[:3]) == list(rc[:3])
+        assert len(np.unique(ofb.data[2, :n])) > 1000
+
+
 # ---- resolve pass -------------------------------------------------------------------------------------------------------
 def _resolve_both(orc, R, scene, exposure=1.0, skybox=None, debug_layer=0):
     ofb, _ = oracle_render(orc, scene)
