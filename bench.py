@@ -717,7 +717,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="binned", choices=["binned", "direct"])
-    ap.add_argument("--in-flight", type=int, default=3, help="independent render contexts (views in flight) per GPU")
+    ap.add_argument("--in-flight", type=int, default=4, help="independent render contexts (views in flight) per GPU")
     ap.add_argument("--mesh-blocks", type=int, default=2, help="mesh-kernel blocks per SM with several contexts in flight (swrb_device_set_mesh_occupancy)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl", "none"], help="N>1: how composites reach rank 0 (none = diagnostic: no exchange)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline frames at N=1")

@@ -26,7 +26,7 @@ __device__ __forceinline__ void reset_draw_state(uint32_t gid, uint32_t stride, 
     if (gid == 0) {
         ctl->lastTriCount = ctl->triCount; ctl->lastBigCount = ctl->bigCount; ctl->lastBinTotal = ctl->binTotal + ctl->superTotal;
         ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0;
-        ctl->workCursor = 0; ctl->superTotal = 0; ctl->visCount = 0; ctl->visCountBack = 0; ctl->cullDone = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0;
+        ctl->workCursor = 0; ctl->superTotal = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0;
     }
     for (uint32_t i = gid; i < numTiles; i += stride) { tileCount[i] = 0; tileCursor[i] = 0; }
     for (uint32_t i = gid; i < 160u; i += stride) { superCount[i] = 0; superCursor[i] = 0; }

@@ -65,7 +65,7 @@ k_gbuffer_begin(ulonglong2* __restrict__ keys, const uint4* __restrict__ depthLa
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (gid == 0) {
         ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0;
-        ctl->workCursor = 0; ctl->superTotal = 0; ctl->visCount = 0; ctl->visCountBack = 0; ctl->cullDone = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0;
+        ctl->workCursor = 0; ctl->superTotal = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0;
     }
     for (uint32_t i = gid; i < numVec; i += stride) {
         const uint4 d = __ldg(depthLayer + i);

@@ -18,7 +18,7 @@ namespace swrb {
 __global__ void __launch_bounds__(256)
 k_overdraw_begin(ulonglong2* __restrict__ counters, uint32_t numVec, DevCtl* __restrict__ ctl) {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0; ctl->workCursor = 0; ctl->superTotal = 0; ctl->visCount = 0; ctl->visCountBack = 0; ctl->cullDone = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0; }
+    if (gid == 0) { ctl->triCount = 0; ctl->bigCount = 0; ctl->binTotal = 0; ctl->numActiveTiles = 0; ctl->alphaCount = 0; ctl->clipCount = 0; ctl->workCursor = 0; ctl->superTotal = 0; ctl->sparseTiles = 0; ctl->denseTiles = 0; }
     for (uint32_t i = gid; i < 2u * numVec; i += stride) counters[i] = make_ulonglong2(0ull, 0ull);
 }
 

@@ -74,9 +74,8 @@ struct swrb_device {
     float4* clipRemap = nullptr;      // ClippedU/ClippedV of clipped alpha-tested pieces (2 float4 per alpha record)
     uint32_t* superEntries = nullptr; // binned: per-super-tile lists of wide triangles (capacity superCap)
     uint64_t superCap = 0;
-    uint2* visList = nullptr;         // mesh kernel: {meshlet, draw} of the work items that survive culling
-    uint64_t visListCap = 0;
-    uint32_t inlineMaxArea = 64;      // FrameParams::inlineMaxArea; measured on B200: 32 / 64 / 128 / 256 px give 347 / 354 / 362 / 587 us per C4 view and 83 / 65 / 65 / 65 us per C2 frame (SWRB_INLINE_AREA in the environment overrides, for experiments)
+    uint32_t inlineMaxArea = 128;     // FrameParams::inlineMaxArea; measured on B200 (profiles/r02_summary.md): 64 / 128 / 256 px give 57.3 / 59.5 / 60.4 Gtri/s on the
+                                      // 64-view C4 batch, 175 / - / 190 us on the Sponza frame, 121 / - / 124 us on the knot (SWRB_INLINE_AREA overrides, for experiments)
     BigItem* bigItems = nullptr;      // direct: (tri, bin) work items
     uint64_t triCap = 0, bigItemCap = 0;
     uint32_t* binEntries = nullptr;
@@ -111,8 +110,16 @@ struct swrb_device {
     swr_meshlet* hostDrawMeshlets = nullptr;   // scratch scene for swrb_draw_meshlets_host
     uint32_t hostDrawCap = 0;
 
-    uint32_t* detileScratch = nullptr;
+    // GetPixels to host memory: the de-tile kernel runs on the device stream into one of kDetileSlots row-major scratch images,
+    // the PCIe copy on a copy stream of its own, so the next frame renders while this one's pixels travel.
+    static const int kDetileSlots = 3;
+    uint32_t* detileScratch[kDetileSlots] = {};
     size_t detileCap = 0;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t detiled[kDetileSlots] = {}, copied[kDetileSlots] = {};
+    bool copyInFlight[kDetileSlots] = {};
+    int detileSlot = 0;
+    bool hostCopiesPending = false;   // swrb_sync also waits for the copy stream
 
     void* l2Scratch = nullptr;
     size_t l2ScratchBytes = 0;
@@ -344,10 +351,12 @@ void swrb_device_destroy(swrb_device* d) {
     cudaSetDevice(d->cudaDevice);
     cudaStreamSynchronize(d->stream);
     cudaFree(d->ctl); cudaFreeHost(d->ctlHost); cudaFree(d->tris); cudaFree(d->trisW); cudaFree(d->clipRemap); cudaFree(d->alphaTris); cudaFree(d->superEntries);
-    cudaFree(d->visList); cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
+    cudaFree(d->bigItems); cudaFree(d->binEntries); cudaFree(d->tileCount); cudaFree(d->drawItems);
     for (int i = 0; i < swrb_device::kStagingSlots; i++) { cudaFreeHost(d->drawStaging[i]); cudaEventDestroy(d->drawStagingDone[i]); }
     cudaFree(d->cullBitmapDev); cudaFree(d->cullUpload); cudaFree(d->visibleDev); cudaFree(d->hostDrawMeshlets);
-    cudaFree(d->detileScratch); cudaFree(d->clipCache); cudaFree(d->peerCounter); cudaFree(d->l2Scratch);
+    for (int i = 0; i < swrb_device::kDetileSlots; i++) { cudaFree(d->detileScratch[i]); if (d->detiled[i]) cudaEventDestroy(d->detiled[i]); if (d->copied[i]) cudaEventDestroy(d->copied[i]); }
+    if (d->copyStream) { cudaStreamSynchronize(d->copyStream); cudaStreamDestroy(d->copyStream); }
+    cudaFree(d->clipCache); cudaFree(d->peerCounter); cudaFree(d->l2Scratch);
     cudaEventDestroy(d->timerBegin); cudaEventDestroy(d->timerEnd);
     if (d->st) {
         for (int s = 0; s < SWRB_STAGE_COUNT_; s++)
@@ -385,6 +394,7 @@ int swrb_sync(swrb_device* d) {
     if (!d) return fail(SWRB_E_INVALID, "device is null");
     CU(cudaSetDevice(d->cudaDevice));
     CU(cudaStreamSynchronize(d->stream));
+    if (d->hostCopiesPending) { CU(cudaStreamSynchronize(d->copyStream)); d->hostCopiesPending = false; }
     return check_overflow(d);
 }
 
@@ -785,23 +795,41 @@ int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, ui
     swrb_device* d = fb->dev;
     CU(cudaSetDevice(d->cudaDevice));
     size_t need = (size_t)fb->width * fb->height;
+    if (!d->copyStream) {
+        CU(cudaStreamCreateWithFlags(&d->copyStream, cudaStreamNonBlocking));
+        for (int i = 0; i < swrb_device::kDetileSlots; i++) {
+            CU(cudaEventCreateWithFlags(&d->detiled[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&d->copied[i], cudaEventDisableTiming));
+        }
+    }
     if (d->detileCap < need) {
-        if (d->detileScratch) CU(cudaFree(d->detileScratch));
-        d->detileScratch = nullptr; d->detileCap = 0;
-        CU(cudaMalloc(&d->detileScratch, need * 4));
+        CU(cudaStreamSynchronize(d->copyStream));
+        for (int i = 0; i < swrb_device::kDetileSlots; i++) {
+            if (d->detileScratch[i]) CU(cudaFree(d->detileScratch[i]));
+            d->detileScratch[i] = nullptr; d->copyInFlight[i] = false;
+        }
+        d->detileCap = 0;
+        for (int i = 0; i < swrb_device::kDetileSlots; i++) CU(cudaMalloc(&d->detileScratch[i], need * 4));
         d->detileCap = need;
     }
-    int rc = swrb_fb_get_pixels_device(fb, layer, d->detileScratch, fb->width);
+    const int slot = d->detileSlot;
+    d->detileSlot = (slot + 1) % swrb_device::kDetileSlots;
+    if (d->copyInFlight[slot]) CU(cudaStreamWaitEvent(d->stream, d->copied[slot], 0));     // the scratch image is free again once its copy has left
+    int rc = swrb_fb_get_pixels_device(fb, layer, d->detileScratch[slot], fb->width);
     if (rc) return rc;
-    CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch, (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->stream));
+    CU(cudaEventRecord(d->detiled[slot], d->stream));
+    CU(cudaStreamWaitEvent(d->copyStream, d->detiled[slot], 0));
+    CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch[slot], (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->copyStream));
+    CU(cudaEventRecord(d->copied[slot], d->copyStream));
+    d->copyInFlight[slot] = true;
+    d->hostCopiesPending = true;
     return SWRB_OK;
 }
 
 int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride) {
     int rc = swrb_fb_get_pixels_async(fb, layer, dst_host, stride);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(fb->dev->stream));
-    return check_overflow(fb->dev);
+    return swrb_sync(fb->dev);
 }
 
 // ---- culling -----------------------------------------------------------------------------------
@@ -1083,7 +1111,7 @@ struct DrawList {
     uint64_t totalWork;          // meshlets over all draws
     bool uniformMatrix;          // every draw uses matrix M0 (the clip cache may stand in for the resolve pass's transform)
     const float* M0;
-    bool anyCull;                // some draw carries a cull bitmap or fused frustum planes (the mesh kernel builds a visible list)
+    bool anyCull;                // some draw carries a cull bitmap or fused frustum planes
     const uint32_t* runStarts = nullptr;   // DeferredShader on a scene that mixes textured and material-less meshlets: first work
     uint32_t numRuns = 0;                  // item of every run of one kind (runStarts[0] == 0); null = the batch is one run
 };
@@ -1146,8 +1174,14 @@ static size_t cull_words_needed(const swrb_draw_desc* draws, uint32_t numDraws) 
     return cullWords;
 }
 
+static void launch_mesh(swrb_device* d, bool binned, uint32_t meshGrid, const swr_meshlet* meshlets, const swr_material* materials, const DrawItem* draws, uint32_t numDraws,
+                        uint32_t totalWork, const FrameParams& fp, unsigned long long* keys, const MeshOut& mo, DevCtl* ctl) {
+    if (binned) k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshlets, materials, draws, numDraws, totalWork, fp, keys, mo, ctl);
+    else k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshlets, materials, draws, numDraws, totalWork, fp, keys, mo, ctl);
+}
+
 static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
-                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid, uint2* visList);
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid);
 
 static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMeshletsDev, const swr_material* materialsDev,
                      const ResolveTexture* texturesDev, bool alphaTest, const DrawList& dl, bool forResolve, uint32_t program) {
@@ -1172,17 +1206,8 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     MeshOut mo;
     mo.tris = d->tris; mo.alphaTris = d->alphaTris; mo.alphaW = d->trisW; mo.triCapacity = (uint32_t)std::min<uint64_t>(d->triCap, 0xFFFFFFFFu);
     mo.tileCount = nullptr; mo.superCount = nullptr; mo.clipList = reinterpret_cast<uint2*>(d->binEntries); mo.clipCache = nullptr;
-    // persistent mesh grid (64 registers -> at most 4 resident blocks per SM). With culling in the batch the kernel first
-    // builds a visible-meshlet list (8 bytes per work item at most).
+    // persistent mesh grid (64 registers -> at most 4 resident blocks per SM)
     const uint32_t meshGrid = grid_for(d, totalWork, kMeshWarps, d->meshBlocksPerSM);
-    uint2* visList = nullptr;
-    if (dl.anyCull) {
-        if (totalWork > d->visListCap) {
-            rc = ensure_buffer((void**)&d->visList, &d->visListCap, totalWork + totalWork / 8, sizeof(uint2));
-            if (rc) return rc;
-        }
-        visList = d->visList;
-    }
 
     // ---- OverdrawShader / DeferredShader: no lazy vis-buffer — straight into the layers
     if (program != SWRB_PROGRAM_VISBUFFER) {
@@ -1204,7 +1229,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
             }
             {
                 StageScope ss(d, SWRB_STAGE_MESH);
-                k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);
+                launch_mesh(d, false, meshGrid, meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
                 d->launches++;
                 if (fp.clipMode == 2u) {
                     k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
@@ -1220,7 +1245,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
             }
         } else {
             mo.alphaTris = d->alphaTris; mo.alphaW = d->trisW;
-            rc = draw_deferred(fb, meshletsDev, materialsDev, texturesDev, dl, fp, mo, meshGrid, visList);
+            rc = draw_deferred(fb, meshletsDev, materialsDev, texturesDev, dl, fp, mo, meshGrid);
             if (rc) return rc;
         }
         CU(cudaGetLastError());
@@ -1269,7 +1294,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
         mo.tileCount = d->tileCount; mo.superCount = d->superCount;
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);
+            launch_mesh(d, true, meshGrid, meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);
             d->launches++;
         }
         {
@@ -1291,7 +1316,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     } else {
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, visList, fp, fb->keys, mo, d->ctl);   // (the bin-entry buffer is idle on this path: it holds the clip list)
+            launch_mesh(d, false, meshGrid, meshletsDev, materialsDev, dl.items, numDraws, (uint32_t)totalWork, fp, fb->keys, mo, d->ctl);   // (the bin-entry buffer is idle on this path: it holds the clip list)
             d->launches++;
             if (fp.clipMode == 2u) {       // Clipper::ClipTriangles: pieces join the record / alpha lists before they are consumed
                 k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,
@@ -1328,7 +1353,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
 // meshlets of one kind: seed the keys with the depth layer, mesh kernel (every surviving triangle -> a record with 1/w
 // and its draw), [clipper], pass 1 (keys), pass 2 (the winners store depth / base colour / packed normal).
 static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
-                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid, uint2* visList) {
+                         const DrawList& dl, FrameParams fp, MeshOut mo, uint32_t meshGrid) {
     swrb_device* d = fb->dev;
     if (!mo.alphaTris || !mo.alphaW) return fail(SWRB_E_CUDA, "DeferredShader: record lists missing");
     const uint32_t numVec = fb->width * fb->height / 4;
@@ -1347,7 +1372,7 @@ static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_
         }
         {
             StageScope ss(d, SWRB_STAGE_MESH);
-            k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshletsDev, materialsDev, dl.items, dl.numDraws, (uint32_t)dl.totalWork, visList, fp, fb->keys, mo, d->ctl);
+            launch_mesh(d, false, meshGrid, meshletsDev, materialsDev, dl.items, dl.numDraws, (uint32_t)dl.totalWork, fp, fb->keys, mo, d->ctl);
             d->launches++;
             if (fp.clipMode == 2u) {
                 k_clip_triangles<<<d->numSMs, 128, 0, d->stream>>>(reinterpret_cast<const uint2*>(d->binEntries), meshletsDev, materialsDev, dl.items, fp,

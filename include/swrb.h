@@ -130,7 +130,9 @@ SWRB_API int swrb_fb_clear_layer(swrb_fb* fb, uint32_t layer, uint32_t value);
 SWRB_API int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host);  /* raw GetLayerData copy */
 SWRB_API int swrb_fb_upload_tiled(swrb_fb* fb, uint32_t layer, const uint32_t* src_host);
 SWRB_API int swrb_fb_get_pixels(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride); /* Framebuffer::GetPixels */
-/* Same without the final synchronisation: dst_host should be pinned; the pixels are valid after swrb_sync(). */
+/* Same without the final synchronisation: dst_host should be pinned; the pixels are valid after swrb_sync(). The de-tile
+ * runs on the device's stream, the PCIe copy on a copy stream of the device (three images in flight), so later frames render
+ * while this one's pixels travel. */
 SWRB_API int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, uint32_t stride);
 SWRB_API int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride); /* same, device dst */
 /* Same, launched on a caller-provided stream (the caller orders it after the producing call with events);
