@@ -123,28 +123,43 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
     const uint32_t warpsTotal = gridDim.x * kMeshWarps;
     uint32_t nProcessed = 0, nRasterized = 0, nClipped = 0;
 
-    for (uint32_t work = fp.workBegin + blockIdx.x * kMeshWarps + (threadIdx.x >> 5); work < fp.workEnd; work += warpsTotal) {
-        const DrawItem& d = find_draw(draws, numDraws, work);
-        const uint32_t meshIdx = work - d.firstWork;
-
-        // ---- ShadeMeshlet: cull bit (Shading.cpp:282-289)
-        if (d.cullBitmap != nullptr) {
-            uint32_t word = d.cullBitmap[meshIdx >> 4];
-            if (((word >> (meshIdx & 15u)) & 1u) == 0) continue;
-        }
-        const swr_meshlet* m = meshlets + (d.meshletOffset + meshIdx);
-        if (d.fusedCull) {                                                      // Shading.cpp:803-809
-            const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(m));        // BoundCenter, BoundRadius
-            float cx = __uint_as_float(hdrA.x), cy = __uint_as_float(hdrA.y), cz = __uint_as_float(hdrA.z);
-            float rad = __uint_as_float(hdrA.w);
-            bool vis = true;
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                float dist = __fadd_rn(__fmaf_rn(cx, d.planes[i][0], __fmaf_rn(cy, d.planes[i][1], __fmul_rn(cz, d.planes[i][2]))), d.planes[i][3]);
-                vis = vis && (dist > -rad);
+    // The warp's work items are base, base + W, base + 2W, ... (W = warps in the grid). 32 of them are TESTED at a time, one per
+    // lane — draw lookup, ShadeMeshlet's cull bit, CullMeshlets' frustum test — so a culled meshlet costs a lane, not a warp
+    // iteration; the survivors (a ballot) are then shaded one after another by the whole warp.
+    for (uint32_t base = fp.workBegin + blockIdx.x * kMeshWarps + (threadIdx.x >> 5); base < fp.workEnd; base += 32u * warpsTotal) {
+      uint32_t myDraw = 0, myMeshIdx = 0;
+      bool vis = false;
+      {
+        const uint64_t cand64 = (uint64_t)base + (uint64_t)lane * warpsTotal;
+        if (cand64 < fp.workEnd) {
+            const uint32_t cand = (uint32_t)cand64;
+            const DrawItem& dc = find_draw(draws, numDraws, cand);
+            myDraw = (uint32_t)(&dc - draws);
+            myMeshIdx = cand - dc.firstWork;
+            vis = true;
+            if (dc.cullBitmap != nullptr) {                                         // ShadeMeshlet: cull bit (Shading.cpp:282-289)
+                const uint32_t word = dc.cullBitmap[myMeshIdx >> 4];
+                vis = ((word >> (myMeshIdx & 15u)) & 1u) != 0;
             }
-            if (!vis) continue;
+            if (vis && dc.fusedCull) {                                              // Shading.cpp:803-809
+                const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(meshlets + (dc.meshletOffset + myMeshIdx)));   // BoundCenter, BoundRadius
+                const float cx = __uint_as_float(hdrA.x), cy = __uint_as_float(hdrA.y), cz = __uint_as_float(hdrA.z);
+                const float rad = __uint_as_float(hdrA.w);
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const float dist = __fadd_rn(__fmaf_rn(cx, dc.planes[i][0], __fmaf_rn(cy, dc.planes[i][1], __fmul_rn(cz, dc.planes[i][2]))), dc.planes[i][3]);
+                    vis = vis && (dist > -rad);
+                }
+            }
         }
+      }
+      uint32_t alive = __ballot_sync(0xFFFFFFFFu, vis);
+      while (alive) {
+        const uint32_t src = (uint32_t)__ffs(alive) - 1u;
+        alive &= alive - 1u;
+        const DrawItem& d = draws[__shfl_sync(0xFFFFFFFFu, myDraw, src)];
+        const uint32_t meshIdx = __shfl_sync(0xFFFFFFFFu, myMeshIdx, src);
+        const swr_meshlet* m = meshlets + (d.meshletOffset + meshIdx);
         // issue every load of the meshlet before anything depends on them
         const uint4 hdrB = __ldg(reinterpret_cast<const uint4*>(m) + 2);        // bytes 32..47: ..., NumVertices, NumTriangles, AlphaCutoff
         const uint32_t materialId = __ldg(reinterpret_cast<const uint32_t*>(m) + 12);
@@ -338,6 +353,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             }
         }
         __syncwarp();
+      }
     }
 
     // ---- perf counters: one atomic per warp per counter (Rasterizer.cpp:927-932 FlushThreadCounters)
