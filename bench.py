@@ -15,7 +15,8 @@ over NVLink, --gather p2p; or an NCCL gather, --gather nccl).
           launching streams, barrier + synchronize on both sides, max over ranks.
   e2e     the same batch through the C ABI with HOST buffers: every step uploads the meshlets from pinned host memory (each
           rank 1/N of them, the rest arrives by NCCL all-gather over NVLink) and every view's resolved image is read back to
-          pinned host memory; two scene buffers so the next step's upload overlaps this step's rendering.
+          pinned host memory; all render contexts take part (their scene copies refreshed device-to-device), two scene buffers each so the
+          next step's upload overlaps this step's rendering.
   parity  before anything is timed every view this rank renders is compared with the committed oracle fixture
           (tests/golden/bench_configs.json: SHA-256 of depth and surface ids, exact) and, where a colour fixture exists,
           with the oracle's resolved image (<= 2/255).
@@ -299,14 +300,11 @@ def run_ours(args):
         r.set_mesh_occupancy(args.mesh_blocks if F > 1 else 4)
         ctxs.append(SimpleNamespace(rast=r, stream=st, fb=r.create_framebuffer(scene.width, scene.height),
                                     scene=r.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights), frames={}))
-    EC = min(2, F)            # contexts that take part in the e2e loop (two scene buffers)
     for i, v in enumerate(mine):
-        for ci, c in enumerate(ctxs):
-            if ci != i % F and ci >= EC:
-                continue
-            batch = c.rast.create_batch(c.scene, workloads.view_draws(c.rast, wl, v))
-            uni = api.Rasterizer.make_uniforms(**workloads.view_uniforms(wl, v))
-            c.frames[i] = (batch, c.rast.make_frame(batch, uni))
+        c = ctxs[i % F]
+        batch = c.rast.create_batch(c.scene, workloads.view_draws(c.rast, wl, v))
+        uni = api.Rasterizer.make_uniforms(**workloads.view_uniforms(wl, v))
+        c.frames[i] = (batch, c.rast.make_frame(batch, uni))
 
     # ---- parity: every view of this rank against the oracle fixture, before anything is timed
     parity = {"views_checked": 0, "visbuffer_exact": 0, "colour_checked": 0, "colour_ok": 0, "worst_colour_err": 0, "mismatches": []}
@@ -505,41 +503,68 @@ def run_ours(args):
     c0.rast.set_mesh_occupancy(args.mesh_blocks if F > 1 else 4)
 
     # ---- e2e: the same batch through the C ABI with HOST buffers. Every step: the scene goes up from pinned host memory (this rank's
-    # 1/N of it, all-gathered over NVLink when N > 1), every view's resolved image comes back to pinned host memory.
+    # 1/N of it, all-gathered over NVLink when N > 1) into a loader context's scene (own stream), is copied on the device to the render contexts' scenes,
+    # and every view's resolved image comes back to pinned host memory. Two scene buffers per context (A/B), so the next step's
+    # upload overlaps this step's rendering; all F contexts render their share of every step.
     chunk = (len(scene.meshlets) + world - 1) // world
     lo, hi = min(rank * chunk, len(scene.meshlets)), min((rank + 1) * chunk, len(scene.meshlets))
     host_meshlets = ctxs[0].rast.alloc_pinned((hi - lo,), scene.meshlets.dtype)
     host_meshlets[...] = scene.meshlets[lo:hi]
     host_images = [ctxs[0].rast.alloc_pinned((scene.height, scene.width), np.uint32) for _ in range(min(len(mine), 8))]
-    scene_tensors = []
-    if world > 1:
-        class _Raw:        # the scene's meshlet array as a torch tensor (zero copy), padded view for an even all-gather
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        for c in ctxs[:EC]:
-            scene_tensors.append(torch.as_tensor(_Raw(c.scene.meshlets_device_ptr(), len(scene.meshlets) * 1728), device="cuda"))
+
+    class _Raw:        # a scene's meshlet array as a torch tensor (zero copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    nbytes = len(scene.meshlets) * 1728
+    # the loader: a context of its own (own stream) that only receives the scene from the host, so uploads never sit between frames
+    loader = SimpleNamespace(rast=api.Rasterizer(local_rank), stream=torch.cuda.Stream())
+    loader.rast.set_stream(loader.stream.cuda_stream)
+    loader.scenes2 = [loader.rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights) for _ in range(2)]
+    loader.tensors2 = [torch.as_tensor(_Raw(sc.meshlets_device_ptr(), nbytes), device="cuda") for sc in loader.scenes2]
+    for c in ctxs:
+        c.scenes2 = [c.scene, c.rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)]
+        c.tensors2 = [torch.as_tensor(_Raw(sc.meshlets_device_ptr(), nbytes), device="cuda") for sc in c.scenes2]
+        c.frames2 = [dict(c.frames), {}]
+        c.copied = [torch.cuda.Event(), torch.cuda.Event()]      # this context's copy of scene buffer b has been made
+    for i, v in enumerate(mine):
+        c = ctxs[i % F]
+        batch = c.rast.create_batch(c.scenes2[1], workloads.view_draws(c.rast, wl, v))
+        c.frames2[1][i] = (batch, c.rast.make_frame(batch, api.Rasterizer.make_uniforms(**workloads.view_uniforms(wl, v))))
+    uploaded = [torch.cuda.Event(), torch.cuda.Event()]
     even = world > 1 and len(scene.meshlets) % world == 0
+    e2e_state = {"steps": 0}
 
     def step_e2e(k):
-        c = ctxs[k % EC]
-        c.rast.sync()                                             # this context's previous step (its images are on the host now)
-        c.scene.update_meshlets(host_meshlets, lo)                # H2D on the context's stream
+        b = k % 2
+        if e2e_state["steps"] >= 2:
+            uploaded[b].synchronize()                             # pace the host: at most two steps ahead of the GPU
+            for c in ctxs:
+                loader.stream.wait_event(c.copied[b])             # nobody still reads the loader's buffer b (device copies of step k - 2)
+        loader.scenes2[b].update_meshlets(host_meshlets, lo)      # H2D on the loader's stream, beside the rendering of step k - 1
         if world > 1:
-            with torch.cuda.stream(c.stream):
-                tsr = scene_tensors[k % EC]
+            with torch.cuda.stream(loader.stream):
+                tsr = loader.tensors2[b]
                 if even:
                     dist.all_gather_into_tensor(tsr, tsr[lo * 1728:hi * 1728])
                 else:
                     parts = [tsr[min(r * chunk, len(scene.meshlets)) * 1728:min((r + 1) * chunk, len(scene.meshlets)) * 1728] for r in range(world)]
                     dist.all_gather(parts, tsr[lo * 1728:hi * 1728])
-            c.scene.touch()
+        uploaded[b].record(loader.stream)
+        for c in ctxs:
+            with torch.cuda.stream(c.stream):
+                c.stream.wait_event(uploaded[b])
+                c.tensors2[b].copy_(loader.tensors2[b], non_blocking=True)   # device-to-device, after this context's own frames of step k - 2
+                c.copied[b].record(c.stream)
+            c.scenes2[b].touch()
         for i in range(len(mine)):
-            batch, frame = c.frames[i]
+            c = ctxs[i % F]
+            batch, frame = c.frames2[b][i]
             frame.PixelsHost = host_images[i % len(host_images)].ctypes.data
-            c.rast.submit_frame(c.fb, frame)                      # clear + draw + resolve + GetPixels (D2H, async)
+            c.rast.submit_frame(c.fb, frame)                      # clear + draw + resolve + GetPixels (D2H, async, on the context's copy stream)
             frame.PixelsHost = None
+        e2e_state["steps"] += 1
 
-    for k in range(2 * EC):
+    for k in range(4):
         step_e2e(k)
     barrier()
     t0e = time.perf_counter()
@@ -602,7 +627,8 @@ def run_ours(args):
                     "views_per_s": round(num_views * args.steps / e2e_s, 1),
                     "note": f"every step: the {scene.meshlets.nbytes / 1e6:.0f} MB of meshlets H2D from pinned host memory (each rank 1/{world} of them"
                             + (", all-gathered over NVLink with NCCL" if world > 1 else "") + f"), {num_views} x (clear + draw + resolve + GetPixels D2H to pinned host memory, "
-                            f"{scene.width * scene.height * 4 / 1e6:.1f} MB per view); {EC} scene buffers so the next step's upload overlaps; wall clock; bytes are whole-job totals"},
+                            f"{scene.width * scene.height * 4 / 1e6:.1f} MB per view) spread over the {F} render contexts of each GPU, whose scene copies are refreshed device-to-device "
+                            "from the uploaded one; two scene buffers per context so the next step's upload overlaps; wall clock; bytes are whole-job totals"},
             "roofline": roofline, "stages": stages,
             "counters_per_step": {"TrianglesProcessed": int(csum[0]), "TrianglesRasterized": int(csum[1]), "TrianglesClipped": int(csum[2]), "BinQueueFlushes": int(csum[3])},
             "draw_stats": draw_stats, "image_xor": checksum,

@@ -819,7 +819,8 @@ int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, ui
     if (rc) return rc;
     CU(cudaEventRecord(d->detiled[slot], d->stream));
     CU(cudaStreamWaitEvent(d->copyStream, d->detiled[slot], 0));
-    CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch[slot], (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->copyStream));
+    if (stride == fb->width) CU(cudaMemcpyAsync(dst_host, d->detileScratch[slot], need * 4, cudaMemcpyDeviceToHost, d->copyStream));
+    else CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch[slot], (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->copyStream));
     CU(cudaEventRecord(d->copied[slot], d->copyStream));
     d->copyInFlight[slot] = true;
     d->hostCopiesPending = true;
