@@ -9,7 +9,7 @@ What differs from the reference, by necessity (none of its third-party importers
   * cgltf -> the JSON + buffer parsing below (`.gltf` with external / data-URI buffers, and `.glb`);
   * meshoptimizer's `meshopt_buildMeshlets` -> `adjacency_order` (grow each meshlet over shared vertices, cheapest
     triangle first) + the cutting scan of `scenes.meshletize` (different meshlet boundaries = different surface ids, same
-    geometry) and a bounding-box sphere instead of `meshopt_computeMeshletBounds`;
+    geometry); `meshopt_computeMeshletBounds` (bounding sphere + normal cone) is restated in `compute_meshlet_bounds`;
   * stb_image -> Pillow for the texture files.
 Everything downstream (the meshlet bytes, materials, texture layout, uniforms) is the reference's format, so an imported
 scene goes through `api.Rasterizer.upload_scene` / the oracle like the procedural ones.
@@ -245,6 +245,68 @@ def adjacency_order(tris: np.ndarray, max_verts: int = 64, max_tris: int = 128) 
     return np.asarray(order, dtype=np.int64)
 
 
+def _bounding_sphere(points: np.ndarray):
+    """meshoptimizer's computeBoundingSphere (clusterizer.cpp, v1.1 as pinned by the reference's CMakeLists.txt:21; restated from
+    the published algorithm, float32 throughout): the extreme points along the three axes give three candidate diameters, the
+    longest becomes the initial sphere, then every point outside pulls the sphere towards itself just far enough to be covered."""
+    pts = np.asarray(points, dtype=f32)
+    pmin, pmax = pts.argmin(axis=0), pts.argmax(axis=0)                      # first index on ties, like the strict compares
+    best_d2, best_axis = f32(0), 0
+    for axis in range(3):
+        d = pts[pmax[axis]] - pts[pmin[axis]]
+        d2 = f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+        if d2 > best_d2:
+            best_d2, best_axis = d2, axis
+    p1, p2 = pts[pmin[best_axis]], pts[pmax[best_axis]]
+    center = ((p1 + p2) / f32(2)).astype(f32)
+    radius = f32(np.sqrt(best_d2) / f32(2))
+    for p in pts:
+        d = p - center
+        d2 = f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])
+        if d2 > radius * radius:
+            dist = f32(np.sqrt(d2))
+            k = f32(0.5) + (radius / dist) / f32(2)
+            center = (center * k + p * (f32(1) - k)).astype(f32)
+            radius = f32((radius + dist) / f32(2))
+    return center, radius
+
+
+def compute_meshlet_bounds(meshlets: np.ndarray) -> None:
+    """meshopt_computeMeshletBounds (Scene.cpp:236-245 stores its result): bounding sphere of the corners of the non-degenerate
+    triangles, and the normal cone — axis = centre of the bounding sphere of the unit triangle normals, cutoff =
+    sqrt(1 - mindp^2) with mindp the smallest normal . axis, apex = centre - axis * max over triangles of
+    dot(centre - corner, n) / dot(axis, n); a cone wider than ~168 degrees (mindp <= 0.1) is stored as cutoff 1 without apex /
+    axis. Writes BoundCenter, BoundRadius, ConeApex, ConeAxis, ConeCutoff in place."""
+    with np.errstate(all="ignore"):
+        for m in meshlets:
+            nt = int(m["NumTriangles"])
+            pos = m["Positions"].T.astype(f32)                                   # [64, 3]
+            idx = m["Indices"][:, :nt].T.astype(np.int64)                        # [nt, 3]
+            corners = pos[idx]                                                   # [nt, 3, 3]
+            normal = np.cross(corners[:, 1] - corners[:, 0], corners[:, 2] - corners[:, 0]).astype(f32)
+            area = np.sqrt((normal * normal).sum(axis=1, dtype=f32)).astype(f32)
+            keep = area > 0
+            m["BoundCenter"], m["BoundRadius"] = 0, 0
+            m["ConeApex"], m["ConeAxis"], m["ConeCutoff"] = 0, 0, 0
+            if not keep.any():
+                continue
+            corners, normal = corners[keep], (normal[keep] / area[keep, None]).astype(f32)
+            center, radius = _bounding_sphere(corners.reshape(-1, 3))
+            ncenter, _ = _bounding_sphere(normal)
+            alen = f32(np.sqrt((ncenter * ncenter).sum(dtype=f32)))
+            axis = (ncenter * (f32(0) if alen == 0 else f32(1) / alen)).astype(f32)
+            mindp = min(f32(1), f32((normal @ axis).min()))
+            m["BoundCenter"], m["BoundRadius"] = center, radius
+            if mindp <= f32(0.1):
+                m["ConeCutoff"] = 1.0
+                continue
+            t = ((center[None, :] - corners[:, 0]) * normal).sum(axis=1, dtype=f32) / (normal @ axis)
+            maxt = max(f32(0), f32(t.max()))
+            m["ConeApex"] = center - axis * maxt
+            m["ConeAxis"] = axis
+            m["ConeCutoff"] = f32(np.sqrt(f32(1) - mindp * mindp))
+
+
 def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Camera | None = None,
                 flip_winding: bool = False) -> SceneData:
     """Scene::ImportGltf. Returns a SceneData (meshlets, one DrawNode per glTF node with a mesh, materials, textures,
@@ -286,6 +348,7 @@ def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Ca
             cursor += len(m)
         ranges.append((start, cursor))
     meshlets = concat_meshlets(parts) if parts else meshletize(np.zeros((0, 3), dtype=f32), np.zeros((0, 3), dtype=np.int64))
+    compute_meshlet_bounds(meshlets)                                           # Scene.cpp:236-245
 
     nodes, lights = [], []
     punctual = js.get("extensions", {}).get("KHR_lights_punctual", {}).get("lights", [])

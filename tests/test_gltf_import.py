@@ -148,6 +148,48 @@ def test_adjacency_order_fills_meshlets_from_a_shuffled_index_buffer():
     assert tri_set(naive) == tri_set(grown)
 
 
+def test_meshlet_bounds_sphere_and_cone():
+    """gltf.compute_meshlet_bounds (meshopt_computeMeshletBounds, Scene.cpp:236-245): the sphere encloses every corner of every
+    non-degenerate triangle and is no larger than the bounding-box sphere; the cone axis / cutoff bound every triangle normal, the
+    apex lies behind every triangle plane; a meshlet whose normals span more than a hemisphere gets cutoff 1."""
+    rng = np.random.default_rng(3)
+    # a bumpy sheet (narrow normal cones) and a closed blob (wide ones)
+    u, v = np.meshgrid(np.linspace(0, 1, 33), np.linspace(0, 1, 33), indexing="xy")
+    sheet = np.stack([u * 4, v * 4, 0.2 * np.sin(u * 5) * np.cos(v * 4)], -1).reshape(-1, 3).astype(np.float32)
+    tris = []
+    for r in range(32):
+        for c in range(32):
+            a, b, d, e = r * 33 + c, r * 33 + c + 1, (r + 1) * 33 + c, (r + 1) * 33 + c + 1
+            tris += [(a, b, d), (b, e, d)]
+    ms = scenes.meshletize(sheet, np.asarray(tris))
+    verts, faces = scenes.icosphere(2)
+    ms = scenes.concat_meshlets([ms, scenes.meshletize((verts * (1 + 0.1 * rng.random((len(verts), 1)))).astype(np.float32), faces)])
+    box = ms.copy()
+    scenes.set_bounds(box)
+    gltf.compute_meshlet_bounds(ms)
+    usable = 0
+    for k in range(len(ms)):
+        nt = int(ms["NumTriangles"][k])
+        pos = ms["Positions"][k].T.astype(np.float64)
+        c = pos[ms["Indices"][k][:, :nt].T.astype(int)]
+        n = np.cross(c[:, 1] - c[:, 0], c[:, 2] - c[:, 0])
+        area = np.linalg.norm(n, axis=1)
+        c, n = c[area > 0], n[area > 0] / area[area > 0, None]
+        centre, radius = ms["BoundCenter"][k].astype(np.float64), float(ms["BoundRadius"][k])
+        assert np.linalg.norm(c.reshape(-1, 3) - centre, axis=1).max() <= radius * (1 + 1e-5)
+        assert radius <= float(box["BoundRadius"][k]) * 1.16        # Ritter-style sphere: within ~15 % of the bbox sphere, usually tighter
+        if ms["ConeCutoff"][k] < 1:
+            usable += 1
+            axis = ms["ConeAxis"][k].astype(np.float64)
+            mindp = (n @ axis).min()
+            assert mindp > 0.1 and abs(np.sqrt(1 - mindp * mindp) - ms["ConeCutoff"][k]) < 1e-4
+            assert (((ms["ConeApex"][k].astype(np.float64) - c[:, 0]) * n).sum(axis=1)).max() < 1e-4
+            # the reference's back-face cone test shape: a camera inside the cone behind the apex sees no front face
+            cam_pos = ms["ConeApex"][k].astype(np.float64) - axis * 3.0
+            assert ((n * (c[:, 0] - cam_pos)).sum(axis=1) > 0).all()
+    assert usable > len(ms) // 3 and (ms["ConeCutoff"] == 1).any()
+
+
 def test_combine_normal_mr_and_emissive_mask():
     n = np.array([[[127, 127, 254, 9], [254, 127, 127, 9]]], dtype=np.uint8)          # +Z and +X normals
     mr = np.array([[[1, 2, 3, 4], [5, 6, 7, 8]]], dtype=np.uint8)
