@@ -22,7 +22,7 @@ import weakref
 
 import numpy as np
 
-from .layout import MESHLET_DTYPE, MATERIAL_DTYPE, LIGHT_DTYPE
+from .layout import MESHLET_DTYPE, PACKED_MESHLET_DTYPE, MATERIAL_DTYPE, LIGHT_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswrb.so")
@@ -43,6 +43,7 @@ EXPORTS = [
     "swrb_device_create", "swrb_device_destroy", "swrb_device_set_stream", "swrb_device_set_flags",
     "swrb_device_reserve", "swrb_sync", "swrb_last_error", "swrb_version", "swrb_get_counters",
     "swrb_reset_counters", "swrb_scene_create", "swrb_scene_update_meshlets", "swrb_scene_destroy",
+    "swrb_scene_create_packed", "swrb_scene_update_packed", "swrb_scene_download_meshlets",
     "swrb_fb_create", "swrb_fb_destroy", "swrb_fb_info", "swrb_fb_clear", "swrb_fb_clear_layer",
     "swrb_fb_download_tiled", "swrb_fb_upload_tiled", "swrb_fb_get_pixels", "swrb_fb_get_pixels_device",
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
@@ -210,7 +211,8 @@ class Scene:
     """Device-resident Scene::{Meshlets, Materials, Textures, Lights} (Scene.h:117-123)."""
 
     def __init__(self, rast: "Rasterizer", meshlets: np.ndarray, materials=None, textures=None, lights=None):
-        assert meshlets.dtype == MESHLET_DTYPE
+        packed = meshlets.dtype == PACKED_MESHLET_DTYPE          # swr_meshlet_packed: decoded on the device at upload
+        assert packed or meshlets.dtype == MESHLET_DTYPE
         self.rast = rast
         self.num_meshlets = len(meshlets)
         meshlets = np.ascontiguousarray(meshlets)
@@ -229,11 +231,12 @@ class Scene:
                 d.MipOffsets[k] = int(t.mip_offsets[k])
             d.Data = data.ctypes.data
         self._h = C.c_void_p()
-        _check(rast.lib.swrb_scene_create(rast._h, _ptr(meshlets), C.c_uint32(len(meshlets)),
-                                          _ptr(materials) if len(materials) else None, C.c_uint32(len(materials)),
-                                          descs if textures else None, C.c_uint32(len(textures)),
-                                          _ptr(lights) if len(lights) else None, C.c_uint32(len(lights)),
-                                          C.byref(self._h)))
+        create = rast.lib.swrb_scene_create_packed if packed else rast.lib.swrb_scene_create
+        _check(create(rast._h, _ptr(meshlets), C.c_uint32(len(meshlets)),
+                      _ptr(materials) if len(materials) else None, C.c_uint32(len(materials)),
+                      descs if textures else None, C.c_uint32(len(textures)),
+                      _ptr(lights) if len(lights) else None, C.c_uint32(len(lights)),
+                      C.byref(self._h)))
         rast._children.add(self)
 
     def set_skybox(self, tex):
@@ -252,7 +255,14 @@ class Scene:
 
     def update_meshlets(self, meshlets: np.ndarray, first: int = 0):
         meshlets = np.ascontiguousarray(meshlets)
-        _check(self.rast.lib.swrb_scene_update_meshlets(self._h, _ptr(meshlets), C.c_uint32(first), C.c_uint32(len(meshlets))))
+        fn = self.rast.lib.swrb_scene_update_packed if meshlets.dtype == PACKED_MESHLET_DTYPE else self.rast.lib.swrb_scene_update_meshlets
+        _check(fn(self._h, _ptr(meshlets), C.c_uint32(first), C.c_uint32(len(meshlets))))
+
+    def download_meshlets(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.num_meshlets - first if count is None else count
+        out = np.zeros(count, dtype=MESHLET_DTYPE)
+        _check(self.rast.lib.swrb_scene_download_meshlets(self._h, _ptr(out), C.c_uint32(first), C.c_uint32(count)))
+        return out
 
     def meshlets_device_ptr(self) -> int:
         """Device address of the scene's meshlet array (num_meshlets x 1728 bytes), for callers that fill it on the device."""

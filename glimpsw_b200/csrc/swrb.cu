@@ -30,6 +30,7 @@
 #include "clip.cuh"
 #include "overdraw.cuh"
 #include "gbuffer.cuh"
+#include "unpack.cuh"
 
 using namespace swrb;
 
@@ -173,6 +174,8 @@ struct swrb_scene {
     bool hasAlphaTest = false;
     // Host copy of "MaterialId == UINT_MAX" per meshlet: DeferredShader treats such meshlets differently (depth only,
     // Shading.cpp:352-355) and a batch that mixes both kinds is drawn as runs of one kind (draw_deferred).
+    swr_meshlet_packed* packedStaging = nullptr;   // device buffer the packed bytes land in before k_unpack_meshlets (swrb_scene_*_packed)
+    uint32_t packedStagingCap = 0;
     std::vector<uint8_t> materialless;
     std::vector<int32_t> materialTextureIds;   // host copy of Material::TextureId
     uint32_t numMaterialless = 0;
@@ -425,11 +428,48 @@ int swrb_reset_counters(swrb_device* d) {
 }
 
 // ---- scene -------------------------------------------------------------------------------------
+static uint32_t packed_material_id(const swr_meshlet_packed& p) { uint32_t id; memcpy(&id, p.Header + offsetof(swr_meshlet, MaterialId), 4); return id; }
+
+// H2D of packed meshlets into the scene's staging buffer + decode into meshlets [first, first + count) (unpack.cuh).
+static int upload_packed(swrb_scene* s, const swr_meshlet_packed* packed, uint32_t first, uint32_t count) {
+    if (count == 0) return SWRB_OK;
+    swrb_device* d = s->dev;
+    if (count > s->packedStagingCap) {
+        CU(cudaStreamSynchronize(d->stream));
+        if (s->packedStaging) CU(cudaFree(s->packedStaging));
+        s->packedStaging = nullptr; s->packedStagingCap = 0;
+        CU(cudaMalloc(&s->packedStaging, (size_t)count * sizeof(swr_meshlet_packed)));
+        s->packedStagingCap = count;
+    }
+    CU(cudaMemcpyAsync(s->packedStaging, packed, (size_t)count * sizeof(swr_meshlet_packed), cudaMemcpyHostToDevice, d->stream));
+    k_unpack_meshlets<<<std::min<uint32_t>(count, (uint32_t)d->numSMs * 16u), 128, 0, d->stream>>>(s->packedStaging, s->meshlets + first, count);
+    d->launches++;
+    CU(cudaGetLastError());
+    return SWRB_OK;
+}
+
+static int scene_create_common(swrb_device* d, const swr_meshlet* meshlets, const swr_meshlet_packed* packed, uint32_t num_meshlets,
+                               const swr_material* materials, uint32_t num_materials, const swr_texture_desc* textures, uint32_t num_textures,
+                               const swr_light* lights, uint32_t num_lights, swrb_scene** out);
+
 int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_meshlets, const swr_material* materials,
                       uint32_t num_materials, const swr_texture_desc* textures, uint32_t num_textures,
                       const swr_light* lights, uint32_t num_lights, swrb_scene** out) {
-    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
     if (num_meshlets && !meshlets) return fail(SWRB_E_INVALID, "meshlets is null");
+    return scene_create_common(d, meshlets, nullptr, num_meshlets, materials, num_materials, textures, num_textures, lights, num_lights, out);
+}
+
+int swrb_scene_create_packed(swrb_device* d, const swr_meshlet_packed* meshlets, uint32_t num_meshlets, const swr_material* materials,
+                             uint32_t num_materials, const swr_texture_desc* textures, uint32_t num_textures,
+                             const swr_light* lights, uint32_t num_lights, swrb_scene** out) {
+    if (num_meshlets && !meshlets) return fail(SWRB_E_INVALID, "meshlets is null");
+    return scene_create_common(d, nullptr, meshlets, num_meshlets, materials, num_materials, textures, num_textures, lights, num_lights, out);
+}
+
+static int scene_create_common(swrb_device* d, const swr_meshlet* meshlets, const swr_meshlet_packed* packed, uint32_t num_meshlets,
+                               const swr_material* materials, uint32_t num_materials, const swr_texture_desc* textures, uint32_t num_textures,
+                               const swr_light* lights, uint32_t num_lights, swrb_scene** out) {
+    if (!d || !out) return fail(SWRB_E_INVALID, "null argument");
     if (num_meshlets >= (1u << 24) - 1u) return fail(SWRB_E_INVALID, "%u meshlets: the visibility key orders at most 2^24 - 2 meshlets per scene", num_meshlets);
     CU(cudaSetDevice(d->cudaDevice));
     CreateGuard<swrb_scene, swrb_scene_destroy> guard{ new swrb_scene() };
@@ -438,10 +478,14 @@ int swrb_scene_create(swrb_device* d, const swr_meshlet* meshlets, uint32_t num_
     s->numMeshlets = num_meshlets;
     s->attrDirtyLo = 0; s->attrDirtyHi = num_meshlets;
     s->materialless.resize(num_meshlets);
-    for (uint32_t i = 0; i < num_meshlets; i++) { s->materialless[i] = meshlets[i].MaterialId == SWR_NO_MATERIAL; s->numMaterialless += s->materialless[i]; }
+    for (uint32_t i = 0; i < num_meshlets; i++) {
+        s->materialless[i] = (meshlets ? meshlets[i].MaterialId : packed_material_id(packed[i])) == SWR_NO_MATERIAL;
+        s->numMaterialless += s->materialless[i];
+    }
     if (num_meshlets) {
         CU(cudaMalloc(&s->meshlets, (size_t)num_meshlets * sizeof(swr_meshlet)));
-        CU(cudaMemcpyAsync(s->meshlets, meshlets, (size_t)num_meshlets * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
+        if (meshlets) CU(cudaMemcpyAsync(s->meshlets, meshlets, (size_t)num_meshlets * sizeof(swr_meshlet), cudaMemcpyHostToDevice, d->stream));
+        else { int rc = upload_packed(s, packed, 0, num_meshlets); if (rc) return rc; }
     }
     s->numMaterials = num_materials;
     if (num_materials) {
@@ -505,6 +549,30 @@ int swrb_scene_update_meshlets(swrb_scene* s, const swr_meshlet* meshlets, uint3
     return SWRB_OK;
 }
 
+int swrb_scene_update_packed(swrb_scene* s, const swr_meshlet_packed* meshlets, uint32_t first, uint32_t count) {
+    if (!s || !meshlets) return fail(SWRB_E_INVALID, "null argument");
+    if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
+    CU(cudaSetDevice(s->dev->cudaDevice));
+    int rc = upload_packed(s, meshlets, first, count);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < count; i++) {
+        const uint8_t ml = packed_material_id(meshlets[i]) == SWR_NO_MATERIAL;
+        s->numMaterialless += (uint32_t)ml - (uint32_t)s->materialless[first + i];
+        s->materialless[first + i] = ml;
+    }
+    CU(cudaStreamSynchronize(s->dev->stream));         // the host array is only borrowed for the call; the staging buffer is reused
+    return swrb_scene_touch(s, first, count);
+}
+
+int swrb_scene_download_meshlets(swrb_scene* s, swr_meshlet* dst_host, uint32_t first, uint32_t count) {
+    if (!s || !dst_host) return fail(SWRB_E_INVALID, "null argument");
+    if ((uint64_t)first + count > s->numMeshlets) return fail(SWRB_E_INVALID, "range [%u,%u) exceeds %u meshlets", first, first + count, s->numMeshlets);
+    CU(cudaSetDevice(s->dev->cudaDevice));
+    CU(cudaMemcpyAsync(dst_host, s->meshlets + first, (size_t)count * sizeof(swr_meshlet), cudaMemcpyDeviceToHost, s->dev->stream));
+    CU(cudaStreamSynchronize(s->dev->stream));
+    return SWRB_OK;
+}
+
 int swrb_scene_meshlets_device(swrb_scene* s, void** out) {
     if (!s || !out) return fail(SWRB_E_INVALID, "null argument");
     *out = s->meshlets;
@@ -551,7 +619,7 @@ void swrb_scene_destroy(swrb_scene* s) {
     cudaSetDevice(s->dev->cudaDevice);
     cudaStreamSynchronize(s->dev->stream);
     if (s->dev->clipCacheMeshlets == s->meshlets) s->dev->clipCacheFb = nullptr;
-    cudaFree(s->meshlets); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights); cudaFree(s->attr); cudaFree(s->skyData);
+    cudaFree(s->meshlets); cudaFree(s->packedStaging); cudaFree(s->materials); cudaFree(s->textures); cudaFree(s->lights); cudaFree(s->attr); cudaFree(s->skyData);
     for (uint32_t* p : s->textureData) cudaFree(p);
     delete s;
 }

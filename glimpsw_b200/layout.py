@@ -22,6 +22,15 @@ MESHLET_DTYPE = np.dtype({
 })
 assert MESHLET_DTYPE.itemsize == 1728
 
+# swr_meshlet_packed (include/swr_types.h): the Meshlet with 16-bit positions inside its own bounding box, 1376 bytes
+PACKED_MESHLET_DTYPE = np.dtype({
+    "names": ["Header", "Origin", "Scale", "Q", "TexCoords", "NormalTangents", "Indices"],
+    "formats": [("u1", 64), ("<f4", 3), ("<f4", 3), ("<u2", (3, 64)), ("<u4", 64), ("<u4", 64), ("u1", (3, 128))],
+    "offsets": [0, 64, 76, 96, 480, 736, 992],
+    "itemsize": 1376,
+})
+assert PACKED_MESHLET_DTYPE.itemsize == 1376
+
 MATERIAL_DTYPE = np.dtype([("TextureId", "<i4"), ("IsDoubleSided", "u1"), ("AlphaCutoff", "u1"), ("_pad", "u1", 2)])
 assert MATERIAL_DTYPE.itemsize == 8
 

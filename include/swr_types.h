@@ -41,6 +41,23 @@ typedef struct swr_meshlet {
     uint8_t  Indices[3][SWR_MAX_PRIMS];
 } swr_meshlet;
 
+/* Packed meshlet — the import-time / transport format of this library for the compression the reference's author
+ * planned (src/SwRast/Shading.cpp:292-294 "TODO: meshlet compression"). Everything but the positions is the Meshlet's bytes
+ * verbatim; the positions are 16-bit fixed point inside the meshlet's own bounding box:
+ *     Positions[a][v] = fmaf((float)Q[a][v], Scale[a], Origin[a])          (one fused multiply-add, IEEE binary32)
+ * 1376 bytes instead of 1728 (positions 384 instead of 768). swrb_scene_create_packed / swrb_scene_update_packed decode it
+ * on the device into the reference layout at upload, so every kernel keeps reading swr_meshlet. */
+typedef struct swr_meshlet_packed {
+    uint8_t  Header[64];                        /* swr_meshlet bytes 0..63: bounds, cone, counts, MaterialId, TangentHandedness */
+    float    Origin[3];
+    float    Scale[3];
+    uint32_t _pad[2];
+    uint16_t Q[3][SWR_MAX_VERTICES];
+    uint32_t TexCoords[SWR_MAX_VERTICES];
+    uint32_t NormalTangents[SWR_MAX_VERTICES];
+    uint8_t  Indices[3][SWR_MAX_PRIMS];
+} swr_meshlet_packed;
+
 /* struct ShadedMeshlet — src/SwRast/Rasterizer.h:82-99 (mesh-shader output). 1472 bytes. */
 typedef struct swr_shaded_meshlet {
     uint8_t PrimCount;
@@ -111,6 +128,8 @@ static_assert(offsetof(swr_meshlet, Positions) == 64, "");
 static_assert(offsetof(swr_meshlet, TexCoords) == 832, "");
 static_assert(offsetof(swr_meshlet, NormalTangents) == 1088, "");
 static_assert(offsetof(swr_meshlet, Indices) == 1344, "");
+static_assert(sizeof(swr_meshlet_packed) == 1376, "packed meshlet layout");
+static_assert(offsetof(swr_meshlet_packed, Q) == 96 && offsetof(swr_meshlet_packed, TexCoords) == 480 && offsetof(swr_meshlet_packed, Indices) == 992, "");
 static_assert(sizeof(swr_shaded_meshlet) == 1472, "ShadedMeshlet layout (Rasterizer.h:82-99)");
 static_assert(offsetof(swr_shaded_meshlet, Indices) == 64, "");
 static_assert(offsetof(swr_shaded_meshlet, Position) == 448, "");

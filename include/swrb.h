@@ -107,6 +107,20 @@ SWRB_API int swrb_scene_create(swrb_device* dev,
                                const swr_light* lights, uint32_t num_lights,
                                swrb_scene** out);
 SWRB_API int swrb_scene_update_meshlets(swrb_scene* scene, const swr_meshlet* meshlets, uint32_t first, uint32_t count);
+/* The same from PACKED meshlets (swr_meshlet_packed, include/swr_types.h: 16-bit positions in the meshlet's bounding box, 1376
+ * instead of 1728 bytes — the "meshlet compression" the reference's author planned at Shading.cpp:292-294, as an import-time /
+ * transport format): the packed bytes cross PCIe, a decode kernel expands them into the reference layout in device memory,
+ * every other call is unchanged. The decoded positions are fmaf((float)Q, Scale, Origin) exactly (oracle: orc_unpack_meshlets),
+ * so results equal those of swrb_scene_create on the host-decoded meshlets bit for bit. */
+SWRB_API int swrb_scene_create_packed(swrb_device* dev,
+                                      const swr_meshlet_packed* meshlets, uint32_t num_meshlets,
+                                      const swr_material* materials, uint32_t num_materials,
+                                      const swr_texture_desc* textures, uint32_t num_textures,
+                                      const swr_light* lights, uint32_t num_lights,
+                                      swrb_scene** out);
+SWRB_API int swrb_scene_update_packed(swrb_scene* scene, const swr_meshlet_packed* meshlets, uint32_t first, uint32_t count);
+/* Reads meshlets [first, first + count) of the scene back from device memory (e.g. to inspect what a packed upload decoded to). */
+SWRB_API int swrb_scene_download_meshlets(swrb_scene* scene, swr_meshlet* dst_host, uint32_t first, uint32_t count);
 /* The scene's meshlet array in device memory (num_meshlets x 1728 bytes), for callers that fill it on the device — e.g.
  * each rank of a multi-GPU job uploads 1/N of the scene from the host and the ranks all-gather the rest over NVLink.
  * After writing, swrb_scene_touch(first, count) tells the library that derived data of that range is stale; the writes

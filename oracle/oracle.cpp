@@ -655,6 +655,21 @@ static void draw_meshlets_impl(uint32_t* color, float* depth, uint32_t* ch2, uin
     }
 }
 
+// Decode of the packed meshlet format (include/swr_types.h: swr_meshlet_packed), the transport format this library adds for
+// the compression planned at Shading.cpp:292-294: every byte but the positions verbatim, position = fmaf(q, Scale, Origin).
+// Parity of a packed scene is defined on these decoded floats: the CUDA decode kernel must reproduce them bit for bit.
+void orc_unpack_meshlets(const swr_meshlet_packed* src, uint32_t count, swr_meshlet* dst) {
+    for (uint32_t m = 0; m < count; m++) {
+        memcpy(&dst[m], src[m].Header, 64);
+        for (int a = 0; a < 3; a++)
+            for (int v = 0; v < SWR_MAX_VERTICES; v++)
+                dst[m].Positions[a][v] = std::fmaf((float)src[m].Q[a][v], src[m].Scale[a], src[m].Origin[a]);
+        memcpy(dst[m].TexCoords, src[m].TexCoords, sizeof(dst[m].TexCoords));
+        memcpy(dst[m].NormalTangents, src[m].NormalTangents, sizeof(dst[m].NormalTangents));
+        memcpy(dst[m].Indices, src[m].Indices, sizeof(dst[m].Indices));
+    }
+}
+
 // Framebuffer::GetPixels — ImageHelpers.cpp:109-147 (de-tile one layer into row-major)
 void orc_fb_get_pixels(const uint32_t* layer, uint32_t width, uint32_t height, uint32_t* dest, uint32_t stride) {
     for (uint32_t y = 0; y < height; y++)

@@ -291,3 +291,13 @@ def set_reciprocal_mode(mode: int) -> bool:
     bit 1: the back-face determinant contracted into one FMA (App. B.1b). Sensitivity studies only
     (tools/rcp14_sensitivity.py). Returns False when bit 0 is asked for on a host without AVX-512F (mode unchanged)."""
     return lib().orc_set_reciprocal_mode(C.c_int(mode)) == 0
+
+
+def unpack_meshlets(packed: np.ndarray) -> np.ndarray:
+    """Decode of swr_meshlet_packed (glimpsw_b200.compress.pack_meshlets) into Meshlets: positions = fmaf(q, Scale, Origin)."""
+    from glimpsw_b200.layout import MESHLET_DTYPE
+    assert packed.dtype.itemsize == 1376
+    packed = np.ascontiguousarray(packed)
+    out = np.zeros(len(packed), dtype=MESHLET_DTYPE)
+    lib().orc_unpack_meshlets(_p(packed), C.c_uint32(len(packed)), _p(out))
+    return out
