@@ -43,7 +43,7 @@ EXPORTS = [
     "swrb_device_create", "swrb_device_destroy", "swrb_device_set_stream", "swrb_device_set_flags",
     "swrb_device_reserve", "swrb_sync", "swrb_last_error", "swrb_version", "swrb_get_counters",
     "swrb_reset_counters", "swrb_scene_create", "swrb_scene_update_meshlets", "swrb_scene_destroy",
-    "swrb_scene_create_packed", "swrb_scene_update_packed", "swrb_scene_download_meshlets",
+    "swrb_scene_create_packed", "swrb_scene_update_packed", "swrb_scene_download_meshlets", "swrb_fb_keys_device", "swrb_fb_keys_touched",
     "swrb_fb_create", "swrb_fb_destroy", "swrb_fb_info", "swrb_fb_clear", "swrb_fb_clear_layer",
     "swrb_fb_download_tiled", "swrb_fb_upload_tiled", "swrb_fb_get_pixels", "swrb_fb_get_pixels_device",
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
@@ -162,6 +162,15 @@ class Framebuffer:
         out = np.empty(self.width * self.height, dtype=np.uint32)
         _check(self.rast.lib.swrb_fb_download_tiled(self._h, C.c_uint32(layer), _ptr(out)))
         return out
+
+    def keys_device(self):
+        """(device pointer, words) of the 64-bit key buffer holding the pending vis-buffer (sort-last composition, swrb.h)."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(self.rast.lib.swrb_fb_keys_device(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def keys_touched(self):
+        _check(self.rast.lib.swrb_fb_keys_touched(self._h))
 
     def upload_tiled(self, layer: int, data: np.ndarray):
         data = np.ascontiguousarray(data, dtype=np.uint32)

@@ -663,6 +663,21 @@ int swrb_fb_info(const swrb_fb* fb, swr_fb_info* out) {
     return SWRB_OK;
 }
 
+int swrb_fb_keys_device(swrb_fb* fb, void** out, uint64_t* numWords) {
+    if (!fb || !out) return fail(SWRB_E_INVALID, "null argument");
+    if (!fb->keys || !fb->visInKeys || fb->layer0IsColor)
+        return fail(SWRB_E_INVALID, "the framebuffer's result is not in its key buffer (draw a vis-buffer batch first, before any resolve or read-back)");
+    *out = fb->keys;
+    if (numWords) *numWords = (uint64_t)fb->width * fb->height;
+    return SWRB_OK;
+}
+
+int swrb_fb_keys_touched(swrb_fb* fb) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    if (fb->dev->clipCacheFb == fb) fb->dev->clipCacheFb = nullptr;     // the keys may name meshlets this device never shaded
+    return SWRB_OK;
+}
+
 // A GetPixels / send on a side stream may still be reading a layer: whatever overwrites the layers on the device's
 // stream waits for it first.
 static int fb_wait_readers(swrb_fb* fb) {

@@ -180,3 +180,72 @@ class PeerComposites:
             consume(views)
         self.collected[slot].record(coll_stream)
         return views
+
+
+# ---- sort-last composition -----------------------------------------------------------------------------
+KEY_SEED_LOW = 0xFFFFFFFF
+KEY_ID_BASE = 0xFFFFFFFE
+
+
+def meshlets_for_rank(num_meshlets: int, rank: int, world: int):
+    """Contiguous share [first, first + count) of a draw's meshlets for `rank` (sort-last: every GPU draws a subset of the scene)."""
+    per = (num_meshlets + world - 1) // world
+    first = min(rank * per, num_meshlets)
+    return first, min(per, num_meshlets - first)
+
+
+def key_rank(surface_id):
+    """Draw-order rank of an accepted (unclipped) triangle from its surface id (csrc/common.cuh::key_rank):
+    meshlet * 256 + packet * 32 + lane."""
+    meshlet, prim = surface_id >> 7, surface_id & 127
+    return (meshlet << 8) | ((prim >> 4) << 5) | (prim & 15)
+
+
+def keys_from_layers(depth_bits, ids):
+    """The key buffer a draw from a cleared (depth 0) framebuffer leaves behind, rebuilt from its depth / id layers
+    (numpy uint32 arrays): depth << 32 | (0xFFFFFFFE - rank) where something was drawn, depth << 32 | 0xFFFFFFFF elsewhere."""
+    import numpy as np
+    depth_bits = np.asarray(depth_bits, dtype=np.uint64)
+    low = np.where(depth_bits != 0, np.uint64(KEY_ID_BASE) - key_rank(np.asarray(ids, dtype=np.uint64)), np.uint64(KEY_SEED_LOW))
+    return ((depth_bits << np.uint64(32)) | low).astype(np.uint64)
+
+
+def layers_from_keys(keys, clear_color: int):
+    """(depth bits, surface ids) a key buffer unpacks to (k_keys_unpack)."""
+    import numpy as np
+    keys = np.asarray(keys, dtype=np.uint64)
+    low = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    rank = np.uint64(KEY_ID_BASE) - low
+    ids = ((rank >> np.uint64(8)) << np.uint64(7)) | ((rank >> np.uint64(1)) & np.uint64(0x70)) | (rank & np.uint64(15))
+    seed = low == np.uint64(KEY_SEED_LOW)
+    return (keys >> np.uint64(32)).astype(np.uint32), np.where(seed, np.uint64(clear_color), ids).astype(np.uint32)
+
+
+def composite_keys(keys_tensor, dst=None):
+    """Element-wise maximum of every rank's key buffer (an int64 view: keys of reverse-Z depths in (0, 1] are positive):
+    all-reduce, or reduce to rank `dst`. In place."""
+    import torch.distributed as dist
+    if dist.get_world_size() == 1:
+        return
+    if dst is None:
+        dist.all_reduce(keys_tensor, op=dist.ReduceOp.MAX)
+    else:
+        dist.reduce(keys_tensor, dst=dst, op=dist.ReduceOp.MAX)
+
+
+def composite_framebuffer(fb, dst=None, stream=None):
+    """Sort-last composite of a framebuffer whose vis-buffer draw is pending in its key buffer (api.Framebuffer): NCCL max over
+    the ranks' keys, in place, on `stream` (a torch stream that is ordered after the draw; default: the current one)."""
+    import torch
+
+    class _Raw:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+    ptr, n = fb.keys_device()
+    t = torch.as_tensor(_Raw(ptr, n), device="cuda")
+    if stream is not None:
+        with torch.cuda.stream(stream):
+            composite_keys(t, dst)
+    else:
+        composite_keys(t, dst)
+    fb.keys_touched()

@@ -139,6 +139,17 @@ SWRB_API void swrb_scene_destroy(swrb_scene* scene);
 SWRB_API int swrb_fb_create(swrb_device* dev, uint32_t width, uint32_t height, uint32_t num_layers, swrb_fb** out);
 SWRB_API void swrb_fb_destroy(swrb_fb* fb);
 SWRB_API int swrb_fb_info(const swrb_fb* fb, swr_fb_info* out);
+/* Sort-last composition: after a draw the framebuffer's result lives in its 64-bit key buffer — one word per
+ * pixel in the 4x4-tiled order, depth bits << 32 | (0xFFFFFFFE - draw-order rank), 0x00000000FFFFFFFF-style seeds where nothing
+ * was drawn — and the maximum of two such words is the fragment the reference's sequential depth test would keep when both
+ * triangles were submitted in one scene. GPUs that each drew a DISJOINT subset of the same scene's meshlets (same framebuffer
+ * size, same clear) therefore composite bit-exactly with an element-wise max of their key buffers (ncclMax on int64: every key
+ * is a positive int64). swrb_fb_keys_device hands out the buffer (width * height words; SWRB_E_INVALID unless a vis-buffer
+ * draw is pending in the keys); after writing the combined keys back, swrb_fb_keys_touched tells the library that the keys no
+ * longer come from this device's last batch alone (the resolve pass then re-derives vertices instead of using its cache).
+ * The caller orders its writes against the device's stream. */
+SWRB_API int swrb_fb_keys_device(swrb_fb* fb, void** device_ptr_out, uint64_t* num_words_out);
+SWRB_API int swrb_fb_keys_touched(swrb_fb* fb);
 SWRB_API int swrb_fb_clear(swrb_fb* fb, uint32_t color, float depth);
 SWRB_API int swrb_fb_clear_layer(swrb_fb* fb, uint32_t layer, uint32_t value);
 SWRB_API int swrb_fb_download_tiled(swrb_fb* fb, uint32_t layer, uint32_t* dst_host);  /* raw GetLayerData copy */

@@ -83,3 +83,75 @@ def test_peer_memory_composite_gather_world2():
     for k in range(7):
         assert got[k] == [all_sums[r][k] for r in range(2)], f"round {k}: gathered composites differ from what the ranks rendered"
     assert all_sums[0] != all_sums[1]          # the two ranks really rendered different views
+
+
+# ---- sort-last composition over NCCL ---------------------------------------------------------------------
+def _sort_last_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from glimpsw_b200 import api, scenes, sharding
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    scene = scenes.torus_knot_scene(120, 48, 960, 540, tex_size=128)
+    rast = api.Rasterizer(rank)
+    rast.set_stream(stream.cuda_stream)
+    gscene = rast.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights)
+    fb = rast.create_framebuffer(scene.width, scene.height)
+    fb.clear(0xFF000000, 0.0)
+    draws = []
+    for node in scene.nodes:                                     # this rank's share of every DrawMeshlets call
+        first, count = sharding.meshlets_for_rank(node.meshlet_count, rank, world)
+        if count:
+            draws.append(dict(offset=node.meshlet_offset + first, count=count, object_to_clip=scene.object_to_clip(node)))
+    rast.draw_batch(fb, gscene, draws)
+    sharding.composite_framebuffer(fb, dst=None, stream=stream)  # ncclAllReduce(max, int64) on the key buffers, in place
+    counters = rast.counters()
+    total = torch.tensor([counters["TrianglesProcessed"], counters["TrianglesRasterized"]], device="cuda")
+    dist.all_reduce(total)
+    if rank == 0:
+        depth, ids = fb.download_tiled(1), fb.download_tiled(0)
+        rast.resolve(fb, gscene, **scenes.resolve_uniforms(scene, scene.nodes[0]))
+        q.put((depth, ids, fb.download_tiled(0), [int(x) for x in total.cpu()]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    rast.destroy()
+    dist.destroy_process_group()
+
+
+def test_sort_last_key_composite_world2():
+    """Two GPUs draw disjoint halves of the scene's meshlets; after an NCCL max over their 64-bit key buffers rank 0 holds the
+    vis-buffer of the whole scene bit for bit (depth, ids, summed counters), and resolves it within the colour tolerance."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from glimpsw_b200 import scenes
+    from oracle import orc
+    from helpers import oracle_render
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sort_last_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    depth, ids, colour, total = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    scene = scenes.torus_knot_scene(120, 48, 960, 540, tex_size=128)
+    orc.build()
+    ofb, oc = oracle_render(orc, scene)
+    n = scene.width * scene.height
+    assert np.array_equal(depth, ofb.data[1, :n]) and np.array_equal(ids, ofb.data[0, :n])
+    assert total == [int(oc[0]), int(oc[1])]
+    orc.resolve(ofb, scene.meshlets, scene.materials, scene.textures, scene.lights, **scenes.resolve_uniforms(scene, scene.nodes[0]))
+    err = np.abs(colour.view(np.uint8).astype(np.int32) - ofb.data[0, :n].view(np.uint8).astype(np.int32))
+    assert err.max() <= 2

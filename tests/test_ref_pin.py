@@ -139,6 +139,23 @@ def test_config2_full_size_bit_exact(orc, R):
     assert list(oc[:3]) == list(rc[:3]) and int(oc[0]) == 999600
 
 
+def test_config4_bench_view_bit_exact(orc, R):
+    """One view of the benchmark batch (BASELINE config C4: 9,994,240 triangles, 126,880 meshlets, 122 draws, frustum-culled by
+    CullMeshlets) at 1920x1080, and its resolved colour."""
+    from glimpsw_b200 import workloads
+    wl = workloads.build("c4_views")
+    scene = wl.scene
+    scene.camera = wl.cameras[21]
+    ofb, oc = oracle_render(orc, scene, cull=True)
+    rfb, rc = ref_render(R, scene, cull=True)
+    assert_same_fb(ofb, rfb, "C4 view 21")
+    assert list(oc[:3]) == list(rc[:3]) and int(oc[0]) > 5_000_000
+    uni = scenes.resolve_uniforms(scene, scene.nodes[0])
+    orc.resolve(ofb, scene.meshlets, scene.materials, scene.textures, scene.lights, **uni)
+    R.resolve(rfb, scene.meshlets, scene.materials, scene.textures, scene.lights, **uni)
+    assert_same_fb(ofb, rfb, "C4 view 21 colour")
+
+
 def test_instanced_scene_with_frustum_cull_and_several_workers(orc, R):
     """C4-style scene (camera inside the lattice): CullMeshlets bitmaps, then the draw, also on 4 worker threads (bins are
     drained independently, so the frame must not depend on the worker count)."""

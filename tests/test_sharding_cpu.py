@@ -112,3 +112,59 @@ def test_slot_protocol_under_random_interleavings(world, slots, frames, seed):
             pc[r] += 1
     assert collected == list(range(frames))
     assert all(p == frames for p in pc)
+
+
+# ---- sort-last composition: max over depth|rank keys == one sequential draw of the whole scene ----------------
+def _sort_last_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import orc
+    from glimpsw_b200 import scenes
+    scene = scenes.instanced_scene(subdivisions=3, instances=9, width=320, height=200)     # overlapping spheres: real depth competition
+    fb = orc.Framebuffer(scene.width, scene.height)
+    fb.clear(0xFF000000, 0.0)
+    for node in scene.nodes:                                     # this rank's contiguous share of every draw
+        first, count = sharding.meshlets_for_rank(node.meshlet_count, rank, world)
+        if count:
+            orc.draw_meshlets(fb, scene.meshlets, node.meshlet_offset + first, count, scene.object_to_clip(node))
+    n = scene.width * scene.height
+    keys = sharding.keys_from_layers(fb.data[1, :n], fb.data[0, :n])
+    assert (keys.view(np.int64) >= 0).all()                      # positive as int64: a signed max is the unsigned max
+    t = torch.from_numpy(keys.view(np.int64).copy())
+    sharding.composite_keys(t)                                   # gloo all-reduce(MAX)
+    if rank == 0:
+        depth, ids = sharding.layers_from_keys(t.numpy().view(np.uint64), 0xFF000000)
+        full = orc.Framebuffer(scene.width, scene.height)
+        full.clear(0xFF000000, 0.0)
+        for node in scene.nodes:
+            orc.draw_meshlets(full, scene.meshlets, node.meshlet_offset, node.meshlet_count, scene.object_to_clip(node))
+        q.put((bool(np.array_equal(depth, full.data[1, :n])), bool(np.array_equal(ids, full.data[0, :n])), int((depth != 0).sum()),
+               int((fb.data[1, :n] != full.data[1, :n]).sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sort_last_key_composite_world2_gloo():
+    """Each rank draws half of every node's meshlets with the oracle; the element-wise max of the two key buffers unpacks to
+    exactly the vis-buffer of the whole scene drawn by one rasterizer (and a single rank's half differs from it)."""
+    assert sharding.meshlets_for_rank(10, 0, 4) == (0, 3) and sharding.meshlets_for_rank(10, 3, 4) == (9, 1) and sharding.meshlets_for_rank(2, 3, 4) == (2, 0)
+    ids = np.array([5 * 128 + 37, 0, 99 * 128 + 127], dtype=np.uint64)
+    d, i = sharding.layers_from_keys(sharding.keys_from_layers(np.array([0x3F000000, 0, 0x3E000000], dtype=np.uint32), ids), 0xAB)
+    assert list(i) == [5 * 128 + 37, 0xAB, 99 * 128 + 127] and list(d) == [0x3F000000, 0, 0x3E000000]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sort_last_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    depth_ok, ids_ok, covered, half_differs = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    assert depth_ok and ids_ok and covered > 5000 and half_differs > 500
