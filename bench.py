@@ -633,6 +633,18 @@ def run_ours(args):
             "counters_per_step": {"TrianglesProcessed": int(csum[0]), "TrianglesRasterized": int(csum[1]), "TrianglesClipped": int(csum[2]), "BinQueueFlushes": int(csum[3])},
             "draw_stats": draw_stats, "image_xor": checksum,
         }
+        wi = traffic.get("warp_instructions")
+        if wi and clocks.get("sm_mhz"):
+            # the kernels are issue-bound, so the roof that explains `value` is the GPU's instruction issue rate: warp instructions
+            # one view executes (ncu smsp__inst_executed.sum of the profiled view, profiles/r02_traffic.json) per second of the timed
+            # region, against 4 schedulers x SMs x the SM clock sampled during that region
+            import torch
+            per_view = float(sum(wi.values()))
+            peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6
+            achieved = per_view / (ms_per_step / num_views * world * 1e-3)
+            line["issue_slots"] = {"warp_instructions_per_view": int(per_view), "achieved_per_s": round(achieved, 1), "peak_per_s": round(peak, 1),
+                                   "frac": round(achieved / peak, 4), "per_kernel": wi,
+                                   "note": "per GPU; instruction counts from the ncu capture of view 0 (profiles/r02_traffic.json), time from this run"}
         if gather_check is not None:
             line["gather_check"] = gather_check
         if configs is not None:
