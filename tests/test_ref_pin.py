@@ -200,6 +200,73 @@ def test_maximum_render_size_and_wrapping_edges(orc, R):
     assert int((ofb.data[1] != 0).sum()) > 1_000_000
 
 
+def test_ragged_fuzz_matches(orc, R):
+    """The ragged generator of tests/test_kat_gpu.py (every vertex / triangle count from empty to full, random windings and
+    repeated indices, sub-pixel to guard-band-sized triangles, vertices behind the camera plane) — 36 seeds over four
+    framebuffer sizes incl. 2896^2 and four triangle-size regimes, in all three raster modes, with and without a double-sided
+    material: vis-buffer and counters identical."""
+    from test_kat_gpu import _ragged_meshlets
+    m4 = np.zeros((4, 4), dtype=np.float32)                      # w = z: vertices with z <= 0 are behind the camera plane
+    m4[0, 0], m4[1, 1], m4[2, 2], m4[2, 3], m4[3, 2] = 1.0, 1.0, 0.0, 1.0, 0.01
+    mats = np.zeros(1, dtype=MATERIAL_DTYPE)
+    mats["IsDoubleSided"], mats["AlphaCutoff"], mats["TextureId"] = 1, 255, -1
+    clipped_total = 0
+    for seed in range(200, 236):
+        spread = [0.3, 1.5, 8.0, 60.0][seed % 4]
+        w, h = [(1000, 564), (640, 360), (1280, 720), (64, 64)][(seed // 4) % 4]
+        if seed == 208:
+            w = h = 2896
+        meshlets = _ragged_meshlets(seed, 41, spread)
+        double_sided = seed % 3 == 0
+        if double_sided:
+            meshlets["MaterialId"] = 0
+        for mode in MODES:
+            ofb = orc.Framebuffer(w, h)
+            ofb.clear(0xFF000000, 0.0)
+            oc = orc.draw_meshlets(ofb, meshlets, 0, len(meshlets), m4, materials=mats if double_sided else None, **mode)
+            rfb = ref.Framebuffer(w, h)
+            rfb.clear(0xFF000000, 0.0)
+            rc = R.draw_meshlets(rfb, meshlets, 0, len(meshlets), m4, materials=mats if double_sided else None, **mode)
+            assert_same_fb(ofb, rfb, f"fuzz seed {seed} {w}x{h} {mode}")
+            assert list(oc[:3]) == list(rc[:3]), (seed, mode, oc[:3], rc[:3])
+            clipped_total += int(oc[2])
+    assert clipped_total > 1000
+
+
+def test_stale_cull_mode_of_material_less_meshlets_is_the_one_deliberate_difference(orc, R):
+    """the reference's binned path reuses one ShadedMeshlet across meshlets (Rasterizer.cpp:521) and
+    ShadeMeshlet only writes CullMode / FragmentShaderId for meshlets WITH a material (Shading.cpp:302-306), so a material-less
+    meshlet inherits the previous meshlet's cull mode on that worker — scheduling-dependent state. The restatement (and the
+    product) use the struct defaults instead (FrontCCW, Rasterizer.h:85-87), which is what the reference's unbinned path does
+    (it constructs a fresh ShadedMeshlet per meshlet, :160). Pinned here so the difference stays exactly this one."""
+    from glimpsw_b200.layout import NO_MATERIAL
+    mats = np.zeros(1, dtype=MATERIAL_DTYPE)
+    mats["IsDoubleSided"], mats["AlphaCutoff"], mats["TextureId"] = 1, 255, -1
+    front = [(-0.8, -0.8, 0.5), (-0.8, -0.2, 0.5), (-0.2, -0.8, 0.5)]
+    back = [(0.2, 0.2, 0.5), (0.8, 0.2, 0.5), (0.2, 0.8, 0.5)]                  # the other winding
+    m = scenes.concat_meshlets([meshlet_from_clip_tris([front], material_id=0), meshlet_from_clip_tris([back], material_id=NO_MATERIAL)])
+
+    def covered(fn, **mode):
+        fb = ref.Framebuffer(64, 64)
+        fb.clear(0xFFFFFFFF, 0.0)
+        c = fn(fb, m, 0, 2, IDENT, materials=mats, **mode)
+        ids = fb.data[0][fb.data[1] != 0]
+        return sorted(set(int(i) >> 7 for i in ids)), int(c[1])
+    drawn = {}
+    for name, mode in zip(MODE_IDS, MODES):
+        drawn[name] = (covered(orc.draw_meshlets, **mode), covered(R.draw_meshlets, **mode))
+    # which of the two windings is the front face is the reference's business; whichever it is, the double-sided meshlet 0 shows
+    assert all(0 in d[0][0] and 0 in d[1][0] for d in drawn.values())
+    # unbinned: the reference agrees with the restatement about meshlet 1
+    assert drawn["direct_clip"][0] == drawn["direct_clip"][1] and drawn["direct_noclip"][0] == drawn["direct_noclip"][1]
+    # binned: if the restatement culls meshlet 1, the reference draws it anyway (inherited CullMode::None); otherwise they agree
+    o, r = drawn["binned"]
+    if 1 not in o[0]:
+        assert r[0] == [0, 1] and r[1] == o[1] + 1
+    else:
+        assert o == r
+
+
 def test_clipped_and_unclipped_depth_ties_in_one_packet(orc, R):
     """Two triangles of one 16-packet with bit-equal depth on shared pixels, one of them crossing the right guard-band
     plane: the reference draws the packet's accepted lanes first and its clipped pieces afterwards (Rasterizer.cpp:181-249),
