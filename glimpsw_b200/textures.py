@@ -149,6 +149,72 @@ def unmap_octahedron(u: np.ndarray, v: np.ndarray):
     return x / n, y / n, z / n
 
 
+def hdr_texture_from_pixels(rgb: np.ndarray, max_levels: int = 8) -> TextureData:
+    """texutil::LoadImageHDR (ImageHelpers.cpp:46-71) minus the file decoder: float RGB pixels [H, W, 3] -> HdrTexture2D
+    (R11G11B10f, truncating pack) with its mip chain."""
+    h, w = rgb.shape[:2]
+    tex = create_texture(w, h, max_levels, 1)
+    rgb = np.asarray(rgb, dtype=f32)
+    set_pixels(tex, pack_r11g11b10f(rgb[..., 0], rgb[..., 1], rgb[..., 2]), 0)
+    generate_mips_hdr(tex)
+    return tex
+
+
+def _sample_linear_hdr_level0(tex: TextureData, u: np.ndarray, v: np.ndarray):
+    """Texture2D<R11G11B10f>::SampleLevel<{Repeat, Linear, Linear}>(u, v, 0, 0) (Texture.h:412-459) with the float branch of
+    SampleLinear (:506-575): 8 fractional bits, the +1 texel not wrapped but faded out (fx = 0) at the right edge, the row
+    below only taken when it is inside the image; float32 in the source's operation order."""
+    W, H = tex.width, tex.height
+    su, sv = u.astype(f32) * f32(W << 8), v.astype(f32) * f32(H << 8)
+    ix = np.rint(su).astype(np.int64) & ((W << 8) - 1)
+    iy = np.rint(sv).astype(np.int64) & ((H << 8) - 1)
+    ixf, iyf = np.maximum(ix - 127, 0), np.maximum(iy - 127, 0)
+    ix, iy = ixf >> 8, iyf >> 8
+    inx, iny = (ix + 1) < W, (iy + 1) < H
+    data = np.asarray(tex.data, dtype=np.uint32)
+    o00 = texel_offset(ix, iy, tex.row_shift)
+    o01 = texel_offset(ix, iy + iny.astype(np.int64), tex.row_shift)
+    lim = len(data) - 1
+    c00, c10 = unpack_r11g11b10f(data[o00]), unpack_r11g11b10f(data[np.minimum(o00 + 8, lim)])
+    c01, c11 = unpack_r11g11b10f(data[o01]), unpack_r11g11b10f(data[np.minimum(o01 + 8, lim)])
+    fx = np.where(inx, (ixf & 255).astype(f32) * f32(1.0 / 256), f32(0))
+    fy = (iyf & 255).astype(f32) * f32(1.0 / 256)
+    out = []
+    for k in range(3):
+        row_a = c00[k] + (c10[k] - c00[k]) * fx
+        row_b = c01[k] + (c11[k] - c01[k]) * fx
+        out.append((row_a + (row_b - row_a) * fy).astype(f32))
+    return out
+
+
+def octahedron_from_panorama(pano_rgb: np.ndarray, max_levels: int = 8) -> TextureData:
+    """texutil::LoadOctahedronFromPanoramaHDR (ImageHelpers.cpp:73-104) minus the file decoder: an equirectangular float RGB
+    panorama [H, W, 3] (power-of-two sizes) -> the octahedron-mapped HdrTexture2D (W x W) ShadingContext::SkyboxTex expects.
+    Per texel: u, v = x / (W - 1) + 0.5 / (W - 1); direction = UnmapOctahedron(u, v); panorama coordinates
+    atan2(dir.z, dir.x) / tau + 0.5, asin(-dir.y) / pi + 0.5; one bilinear sample of the panorama's level 0; truncating pack."""
+    pano = hdr_texture_from_pixels(pano_rgb, 1)
+    face = pano.width
+    cube = create_texture(face, face, max_levels, 1)
+    scale = f32(1.0) / f32(face - 1)
+    center = f32(0.5) * scale
+    coord = (np.arange(face, dtype=np.int64).astype(f32) * scale + center).astype(f32)
+    v, u = np.meshgrid(coord, coord, indexing="ij")
+    # UnmapOctahedron in float32, canonical approx_rsqrt = 1 / sqrt (Texture.h:289-296, SIMD.h:439)
+    x, y = u * f32(2) - f32(1), v * f32(2) - f32(1)
+    z = (f32(1) - np.abs(x) - np.abs(y)).astype(f32)
+    t = np.maximum(-z, f32(0))
+    x, y = (x - np.copysign(t, x)).astype(f32), (y - np.copysign(t, y)).astype(f32)
+    dot = (x * x + (y * y + z * z)).astype(f32)                  # fma chain of simd::dot; the difference is below the 6-bit mantissa
+    r = (f32(1) / np.sqrt(dot)).astype(f32)
+    x, y, z = x * r, y * r, z * r
+    pu = (np.arctan2(z, x).astype(f32) / f32(6.283185307179586) + f32(0.5)).astype(f32)
+    pv = (np.arcsin(np.clip(-y, -1, 1)).astype(f32) / f32(3.141592653589793) + f32(0.5)).astype(f32)
+    rgb = _sample_linear_hdr_level0(pano, pu, pv)
+    set_pixels(cube, pack_r11g11b10f(*rgb), 0)
+    generate_mips_hdr(cube)
+    return cube
+
+
 def procedural_sky_texture(size: int = 256, sun_dir=(0.4, 0.7, 0.6), max_levels: int = 6) -> TextureData:
     """An octahedron-mapped HDR sky (stand-in for the reference's panorama -> octahedron import, the HDR files are not in
     the checkout): horizon-to-zenith gradient, a ground tint and an HDR sun lobe well above 1.0."""

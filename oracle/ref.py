@@ -159,3 +159,14 @@ def probe_triangle(verts, width: int, height: int, cull_mode: int = 1, guardband
     zw = np.zeros(7, dtype=np.float32)
     keep = lib(fast).ref_probe_triangle(_p(v), width, height, cull_mode, 1 if guardband else 0, C.byref(cc), _p(pos), _p(bbox), _p(edges), _p(zw))
     return dict(keep=int(keep), cc=cc.value, pos=pos, bbox=bbox, edges=edges, zw=zw)
+
+
+def octahedron_from_panorama(pano_tex, cube_tex) -> np.ndarray:
+    """LoadOctahedronFromPanoramaHDR on an in-memory panorama texture (glimpsw_b200.textures.TextureData, R11G11B10f); returns the
+    texel array of the octahedron map laid out like `cube_tex`."""
+    pd, keep_p = _texture_descs([pano_tex])
+    cd, keep_c = _texture_descs([cube_tex])
+    out = np.zeros_like(keep_c[0])
+    rc = lib().ref_octahedron_from_panorama(pd, cd, _p(out))
+    assert rc == 0
+    return out

@@ -15,6 +15,7 @@
 //   ref_downsample_depth  texutil::DownsampleDepth                ImageHelpers.cpp:150-247
 //   ref_fb_get_pixels     Framebuffer::GetPixels                  ImageHelpers.cpp:109-147
 //   ref_generate_mips     Texture2D::GenerateMips / GenerateMip   Texture.h:391-397, :577-597
+//   ref_octahedron_from_panorama  texutil::LoadOctahedronFromPanoramaHDR  ImageHelpers.cpp:73-104 (loop re-typed around the reference's pieces)
 //   ref_probe_triangle    Clipper::ComputeClipCodes, TrianglePacket::Setup, GetRenderBoundingBox, TriangleEdgeVars::Setup
 //                         on a packet whose lane 0 holds the probe triangle (Rasterizer.cpp:257-397)
 #include <cstdint>
@@ -231,6 +232,39 @@ int ref_sample_implicit_lod_4x4(const swr_texture_desc* t, const float* u, const
     constexpr swr::SamplerDesc sd = { .Wrap = swr::WrapMode::Repeat, .MagFilter = swr::FilterMode::Linear, .MinFilter = swr::FilterMode::Nearest };
     v_uint c = tex->SampleImplicitLod<sd>(simd::load<v_float>(u), simd::load<v_float>(v));
     memcpy(out, &c, 64);
+    return 0;
+}
+
+// texutil::LoadOctahedronFromPanoramaHDR (ImageHelpers.cpp:73-104) on a panorama that is already an HdrTexture2D in memory (the
+// file decoder is not in this image): the loop below is that function's, calling the reference's own UnmapOctahedron,
+// SampleLevel<PanoSampler>, WriteTile (Pack) and GenerateMips. `cube` describes the output texture (face x face, its mip chain).
+int ref_octahedron_from_panorama(const swr_texture_desc* pano, const swr_texture_desc* cube, uint32_t* cubeData) {
+    auto panoTex = make_texture<swr::HdrTexture2D>(*pano);
+    if (!panoTex) return -1;
+    swr_texture_desc d = *cube;
+    std::vector<uint32_t> zeros((size_t)d.LayerStride * d.NumLayers, 0);
+    d.Data = zeros.data();
+    auto cubeTex = make_texture<swr::HdrTexture2D>(d);
+    if (!cubeTex) return -1;
+    const uint32_t faceSize = panoTex->Width;
+    constexpr swr::SamplerDesc PanoSampler = { .Wrap = swr::WrapMode::Repeat, .MagFilter = swr::FilterMode::Linear, .MinFilter = swr::FilterMode::Linear };
+    float scaleUV = 1.0f / (faceSize - 1);
+    float centerUV = 0.5f * scaleUV;
+    for (uint32_t y = 0; y < faceSize; y += 4) {
+        for (uint32_t x = 0; x < faceSize; x += 4) {
+            v_float u = simd::conv<float>((int32_t)x + swr::TilePixelOffsetsX) * scaleUV + centerUV;
+            v_float v = simd::conv<float>((int32_t)y + swr::TilePixelOffsetsY) * scaleUV + centerUV;
+            v_float3 dir = swr::texutil::UnmapOctahedron({ u, v });
+            for (uint32_t i = 0; i < simd::vec_width; i++) {
+                u[i] = atan2f(dir.z[i], dir.x[i]) / simd::tau + 0.5f;
+                v[i] = asinf(-dir.y[i]) / simd::pi + 0.5f;
+            }
+            v_float3 tile = panoTex->SampleLevel<PanoSampler>(u, v, 0, 0);
+            cubeTex->WriteTile(tile, x, y);
+        }
+    }
+    cubeTex->GenerateMips();
+    memcpy(cubeData, cubeTex->Data, (size_t)d.LayerStride * d.NumLayers * 4);
     return 0;
 }
 

@@ -95,3 +95,54 @@ def test_skybox_resolve_in_tolerance(orc, rast_factory, read_back_first):
     gscene.set_skybox(None)
     rast.resolve(gfb2, gscene, **uni)
     assert np.all(gfb2.download_tiled(0)[is_sky] == 0xFF000000)
+
+
+# ---- panorama -> octahedron import (texutil::LoadOctahedronFromPanoramaHDR, ImageHelpers.cpp:73-104) -------------------------
+def _test_panorama(h=128, w=256):
+    v, u = np.meshgrid((np.arange(h) + 0.5) / h, (np.arange(w) + 0.5) / w, indexing="ij")
+    theta, phi = (u - 0.5) * 2 * np.pi, (v - 0.5) * np.pi
+    r = 0.3 + 0.5 * (0.5 + 0.5 * np.sin(theta * 2)) + 6 * np.exp(-((theta - 1.0) ** 2 + (phi + 0.4) ** 2) * 30)      # an HDR sun lobe
+    g = 0.4 + 0.4 * (0.5 + 0.5 * np.cos(phi * 3))
+    b = 0.6 + 0.3 * (0.5 + 0.5 * np.sin(theta + phi))
+    return np.stack([r, g, b], -1).astype(np.float32)
+
+
+def test_octahedron_from_panorama_looks_up_the_panorama(orc):
+    """Sampling the imported octahedron map in direction d gives the panorama's colour at (atan2(d.z, d.x) / tau + 0.5,
+    asin(-d.y) / pi + 0.5), up to the two bilinear filters and the 6-bit mantissas in between."""
+    pano = _test_panorama()
+    sky = tx.octahedron_from_panorama(pano, 6)
+    assert (sky.width, sky.height, sky.mip_levels) == (256, 256, 6)
+    rng = np.random.default_rng(4)
+    worst, errs = 0.0, []
+    for _ in range(200):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        if abs(d[1]) > 0.95:
+            continue                                                   # the panorama's poles are a single stretched row
+        got = orc.sample_skybox(sky, d)                                # level 1 of the map, bilinear
+        pu, pv = np.arctan2(d[2], d[0]) / (2 * np.pi) + 0.5, np.arcsin(-d[1]) / np.pi + 0.5
+        x, y = pu * 256 - 0.5, pv * 128 - 0.5
+        x0, y0 = int(np.floor(x)) % 256, int(np.clip(np.floor(y), 0, 126))
+        fx, fy = x - np.floor(x), np.clip(y - y0, 0, 1)
+        want = ((pano[y0, x0] * (1 - fx) + pano[y0, (x0 + 1) % 256] * fx) * (1 - fy)
+                + (pano[y0 + 1, x0] * (1 - fx) + pano[y0 + 1, (x0 + 1) % 256] * fx) * fy)
+        errs.append(float(np.max(np.abs(got - want) / (want + 0.05))))
+    # (the sample is level 1 of the map: a 2 x 2 average, which smooths the sun lobe's flank)
+    assert max(errs) < 0.25 and float(np.median(errs)) < 0.03, (max(errs), float(np.median(errs)))
+
+
+def test_octahedron_from_panorama_matches_the_reference_pieces():
+    """The same import with the loop of ImageHelpers.cpp:73-104 around the reference's own UnmapOctahedron / SampleLevel /
+    WriteTile / GenerateMips (oracle/_ref): every texel of every mip level identical."""
+    try:
+        from oracle import ref
+        if not ref.available():
+            raise RuntimeError
+    except Exception:
+        pytest.skip("reference sources / prebuilt oracle/_ref not on this machine")
+    pano = _test_panorama()
+    sky = tx.octahedron_from_panorama(pano, 6)
+    want = ref.octahedron_from_panorama(tx.hdr_texture_from_pixels(pano, 1), sky)
+    n = sky.layer_stride
+    assert np.array_equal(np.asarray(sky.data, dtype=np.uint32)[:n], want[:n])
