@@ -533,6 +533,7 @@ def run_ours(args):
     uploaded = [torch.cuda.Event(), torch.cuda.Event()]
     even = world > 1 and len(scene.meshlets) % world == 0
     e2e_state = {"steps": 0}
+    skip = set()                                                  # --e2e-diag: the legs left out of a diagnostic pass
 
     def step_e2e(k):
         b = k % 2
@@ -540,8 +541,9 @@ def run_ours(args):
             uploaded[b].synchronize()                             # pace the host: at most two steps ahead of the GPU
             for c in ctxs:
                 loader.stream.wait_event(c.copied[b])             # nobody still reads the loader's buffer b (device copies of step k - 2)
-        loader.scenes2[b].update_meshlets(host_meshlets, lo)      # H2D on the loader's stream, beside the rendering of step k - 1
-        if world > 1:
+        if "h2d" not in skip:
+            loader.scenes2[b].update_meshlets(host_meshlets, lo)  # H2D on the loader's stream, beside the rendering of step k - 1
+        if world > 1 and "gather" not in skip:
             with torch.cuda.stream(loader.stream):
                 tsr = loader.tensors2[b]
                 if even:
@@ -553,13 +555,15 @@ def run_ours(args):
         for c in ctxs:
             with torch.cuda.stream(c.stream):
                 c.stream.wait_event(uploaded[b])
-                c.tensors2[b].copy_(loader.tensors2[b], non_blocking=True)   # device-to-device, after this context's own frames of step k - 2
+                if "d2d" not in skip:
+                    c.tensors2[b].copy_(loader.tensors2[b], non_blocking=True)   # device-to-device, after this context's own frames of step k - 2
                 c.copied[b].record(c.stream)
-            c.scenes2[b].touch()
-        for i in range(len(mine)):
+            if "d2d" not in skip:
+                c.scenes2[b].touch()
+        for i in range(len(mine) if "render" not in skip else 0):
             c = ctxs[i % F]
             batch, frame = c.frames2[b][i]
-            frame.PixelsHost = host_images[i % len(host_images)].ctypes.data
+            frame.PixelsHost = host_images[i % len(host_images)].ctypes.data if "d2h" not in skip else None
             c.rast.submit_frame(c.fb, frame)                      # clear + draw + resolve + GetPixels (D2H, async, on the context's copy stream)
             frame.PixelsHost = None
         e2e_state["steps"] += 1
@@ -577,6 +581,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = tris * num_views * args.steps / e2e_s / 1e6
+    if args.e2e_diag:                                             # which leg of the e2e step costs what: the same loop with one leg left out
+        for legs in ((), ("h2d",), ("gather",), ("d2d",), ("d2h",), ("render",), ("h2d", "gather", "d2d"), ("h2d", "gather", "d2d", "d2h")):
+            skip.clear(); skip.update(legs)
+            for k in range(4):
+                step_e2e(k)
+            barrier()
+            t0d = time.perf_counter()
+            for k in range(args.steps):
+                step_e2e(k)
+            barrier()
+            if rank == 0:
+                print(f"[e2e-diag] without {'+'.join(legs) or 'nothing'}: {(time.perf_counter() - t0d) / args.steps * 1e3:.3f} ms/step", file=sys.stderr, flush=True)
+        skip.clear()
     checksum = int(np.bitwise_xor.reduce(host_images[0].reshape(-1)))
 
     # ---- N = 1 only: the other BASELINE configs, and the CPU baseline on the host cores
@@ -761,6 +778,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline frames at N=1")
     ap.add_argument("--ref-views", type=int, default=4, help="--impl reference: views of the batch rendered per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-diag", action="store_true", help="after the e2e leg, time it again with one leg left out at a time (stderr)")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1/C2/C3/C5) at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
