@@ -395,6 +395,7 @@ def run_ours(args):
         sampler.start()
     launches0 = sum(c.rast.launch_count() for c in ctxs)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nvl0 = nvlink_kib(local_rank) if (rank == 0 and world > 1) else None     # rank 0's NVLink byte counters around the timed region
     barrier()
     t_wall0 = time.perf_counter()
     t0.record(ctxs[0].stream)
@@ -417,6 +418,7 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = sum(c.rast.launch_count() for c in ctxs) - launches0
     clocks = sampler.stop()
+    nvl1 = nvlink_kib(local_rank) if nvl0 else None
     total_ms = t0.elapsed_time(t1)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -427,6 +429,13 @@ def run_ours(args):
         launches = int(lt.item())
     ms_per_step = total_ms / args.steps
     value = tris * num_views / (ms_per_step * 1e-3) / 1e6
+    nvlink = {"unavailable": "nvidia-smi nvlink -gt d reports no data counters (N/A) on this box"} if (rank == 0 and world > 1) else None
+    if nvl0 and nvl1:
+        rx, tx = (nvl1[0] - nvl0[0]) * 1024, (nvl1[1] - nvl0[1]) * 1024
+        expect = (num_views - len(mine)) * scene.width * scene.height * 4 * args.steps if gather_kind in ("p2p", "nccl") else 0
+        nvlink = {"rank0_rx_bytes": int(rx), "rank0_tx_bytes": int(tx), "rank0_rx_GBs": round(rx / (total_ms * 1e-3) / 1e9, 1),
+                  "expected_composite_bytes": int(expect), "links": nvl0[2], "link_peak_GBs_per_direction": 900.0,
+                  "source": "nvidia-smi nvlink -gt d on rank 0's GPU, sampled before and after the timed region"}
 
     # ---- the gathered composites are the producers' images (N > 1): checksum of the last round on both sides
     gather_check = None
@@ -664,6 +673,8 @@ def run_ours(args):
                                    "note": "per GPU; instruction counts from the ncu capture of view 0 (profiles/r02_traffic.json), time from this run"}
         if gather_check is not None:
             line["gather_check"] = gather_check
+        if nvlink is not None:
+            line["nvlink"] = nvlink
         if configs is not None:
             line["configs"] = configs
         if cpu:
@@ -763,6 +774,21 @@ def run_reference(args):
         "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
     base.close()
+
+
+def nvlink_kib(index):
+    """(rx KiB, tx KiB, links) summed over the NVLinks of one GPU (`nvidia-smi nvlink -gt d`), or None when the counters are not exposed."""
+    import re
+    try:
+        import torch
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", uuid if uuid.startswith("GPU-") else "GPU-" + uuid],
+                             capture_output=True, text=True, timeout=20).stdout
+        rx = [int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+        tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+        return (sum(rx), sum(tx), len(rx)) if rx and tx else None
+    except Exception:
+        return None
 
 
 def main():
