@@ -45,6 +45,7 @@ EXPORTS = [
     "swrb_reset_counters", "swrb_scene_create", "swrb_scene_update_meshlets", "swrb_scene_destroy",
     "swrb_scene_create_packed", "swrb_scene_update_packed", "swrb_scene_download_meshlets", "swrb_fb_keys_device", "swrb_fb_keys_touched",
     "swrb_fb_create", "swrb_fb_destroy", "swrb_fb_info", "swrb_fb_clear", "swrb_fb_clear_layer",
+    "swrb_fb_set_scissor_rows", "swrb_fb_get_scissor_rows",
     "swrb_fb_download_tiled", "swrb_fb_upload_tiled", "swrb_fb_get_pixels", "swrb_fb_get_pixels_device",
     "swrb_cull_meshlets", "swrb_frustum_planes", "swrb_draw_meshlets", "swrb_draw_batch",
     "swrb_draw_meshlets_host", "swrb_resolve", "swrb_timer_begin", "swrb_timer_end", "swrb_flush_l2",
@@ -153,6 +154,15 @@ class Framebuffer:
 
     def clear(self, color: int, depth: float):
         _check(self.rast.lib.swrb_fb_clear(self._h, C.c_uint32(color), C.c_float(depth)))
+
+    def set_scissor_rows(self, y0: int = 0, y1: int = 0):
+        """Only rows [y0, y1) are drawn, resolved and read back from now on (sort-first split, swrb.h); (0, 0) = the whole framebuffer."""
+        _check(self.rast.lib.swrb_fb_set_scissor_rows(self._h, C.c_uint32(y0), C.c_uint32(y1)))
+
+    def scissor_rows(self) -> tuple[int, int]:
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        _check(self.rast.lib.swrb_fb_get_scissor_rows(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def clear_layer(self, layer: int, value: int):
         _check(self.rast.lib.swrb_fb_clear_layer(self._h, C.c_uint32(layer), C.c_uint32(value)))

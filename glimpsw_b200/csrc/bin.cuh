@@ -25,7 +25,7 @@ constexpr int kScatterThreads = 256;
 __device__ __forceinline__ uint32_t tile_range(const TriRecord& t, const FrameParams& fp,
                                                uint32_t& tx0, uint32_t& ty0, uint32_t& tx1, uint32_t& ty1) {
     BBox r;
-    if (!raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) return 0;
+    if (!raster_region(t.pos0, t.pos1, t.pos2, fp, r)) return 0;
     tx0 = (uint32_t)(r.minX >> kTileShift); ty0 = (uint32_t)(r.minY >> kTileShift);
     tx1 = (uint32_t)((r.maxX - 1) >> kTileShift); ty1 = (uint32_t)((r.maxY - 1) >> kTileShift);
     return (tx1 - tx0 + 1) * (ty1 - ty0 + 1);

@@ -116,6 +116,7 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
             ref_render_bbox(pos[0], pos[1], pos[2], fp.halfW, fp.halfH, bbMin, bbMax);
             if (!(det > 0.0f && lo16(bbMin) < lo16(bbMax) && hi16(bbMin) < hi16(bbMax))) continue;   // :269, :283
             nRasterized++;                                                      // :247
+            if (hi16(bbMax) <= fp.bandY0 || hi16(bbMin) >= fp.bandY1) continue;   // no pixel inside the scissor rows
 
             const uint4 recA = make_uint4(pos[0], pos[1], pos[2], __float_as_uint(nz[0]));
             if (fsId && alphaTris != nullptr) {

@@ -104,7 +104,7 @@ __device__ __forceinline__ const DrawItem& find_draw(const DrawItem* draws, uint
     return draws[lo];
 }
 
-template <bool kBinned>
+template <bool kBinned, bool kBand>   // kBand: the framebuffer has scissor rows (swrb_fb_set_scissor_rows); the plain frame pays nothing for them
 // Persistent grid of 1..4 blocks per SM (swrb_device_set_mesh_occupancy): 4 = the whole register file for a lone frame,
 // 1 leaves room for other render contexts' resolve blocks, whose issue-bound warps fill what these latency-bound ones leave idle.
 __global__ void __launch_bounds__(kMeshWarps * 32, 4)      // 64 registers: up to 4 blocks = 32 warps per SM
@@ -149,6 +149,22 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                 for (int i = 0; i < 5; i++) {
                     const float dist = __fadd_rn(__fmaf_rn(cx, dc.planes[i][0], __fmaf_rn(cy, dc.planes[i][1], __fmul_rn(cz, dc.planes[i][2]))), dc.planes[i][3]);
                     vis = vis && (dist > -rad);
+                }
+            }
+            if (kBand && vis) {
+                // scissor rows: the band is the slab bandNdcLo <= y/w <= bandNdcHi, i.e. the object-space half-spaces
+                // (row_y - lo * row_w) . p >= 0 and (hi * row_w - row_y) . p >= 0 of this draw's ObjectToClip; a meshlet whose
+                // bound sphere lies wholly outside one of them has no pixel in the band (conservative: the slab is a pixel row wider)
+                const float* Mc = fp.uniformMatrix ? fp.M : dc.M;
+                const uint4 hdrA = __ldg(reinterpret_cast<const uint4*>(meshlets + (dc.meshletOffset + myMeshIdx)));
+                const float cx = __uint_as_float(hdrA.x), cy = __uint_as_float(hdrA.y), cz = __uint_as_float(hdrA.z);
+                const float rad = __uint_as_float(hdrA.w) * 1.0001f;
+#pragma unroll
+                for (int side = 0; side < 2; side++) {
+                    const float k = side ? fp.bandNdcHi : fp.bandNdcLo, sgn = side ? -1.0f : 1.0f;
+                    const float a = sgn * (Mc[1] - k * Mc[3]), b = sgn * (Mc[5] - k * Mc[7]), c = sgn * (Mc[9] - k * Mc[11]), dd = sgn * (Mc[13] - k * Mc[15]);
+                    const float len = sqrtf(a * a + b * b + c * c);
+                    vis = vis && (a * cx + b * cy + c * cz + dd > -rad * len);
                 }
             }
         }
@@ -259,7 +275,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     keep = det > 0.0f && lo16(bbMin) < lo16(bbMax) && hi16(bbMin) < hi16(bbMax);   // :269, :283
                     if (keep) {
                         BBox r;
-                        if (raster_region(p0, p1, p2, fp.halfW, fp.halfH, r)) {     // else: counted, touches no pixel
+                        if (raster_region<kBand>(p0, p1, p2, fp, r)) {     // else: counted, touches no pixel
                             const int32_t area = (r.maxX - r.minX) * (r.maxY - r.minY);
                             if (fsId == 0 && (uint32_t)area <= fp.inlineMaxArea && fp.program == 0u) {
                                 TriRecord t;
@@ -332,7 +348,7 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
                     dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), rankBase | ((prim >> 4) << 5) | (prim & 15u), 0u);
                     if (kBinned) {
                         BBox r;
-                        raster_region(p0, p1, p2, fp.halfW, fp.halfH, r);
+                        raster_region<kBand>(p0, p1, p2, fp, r);
                         tx0 = (uint32_t)(r.minX >> kTileShift); ty0 = (uint32_t)(r.minY >> kTileShift);
                         tx1 = (uint32_t)((r.maxX - 1) >> kTileShift); ty1 = (uint32_t)((r.maxY - 1) >> kTileShift);
                     }

@@ -38,7 +38,7 @@ k_raster_overdraw(const TriRecord* __restrict__ tris, FrameParams fp, unsigned l
         t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
         t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
         BBox r;
-        if (!raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) continue;
+        if (!raster_region(t.pos0, t.pos1, t.pos2, fp, r)) continue;
         Edges e;
         edge_setup(t, fp.halfW, fp.halfH, e);
         // fragments overlapping the region; every fragment with a covered pixel is among them, and all of them lie

@@ -33,7 +33,7 @@ k_raster_direct(const TriRecord* __restrict__ tris, FrameParams fp, unsigned lon
         t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
 
         BBox r;
-        if (!raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) continue;
+        if (!raster_region(t.pos0, t.pos1, t.pos2, fp, r)) continue;
         int32_t w = r.maxX - r.minX, h = r.maxY - r.minY;
         if (w * h > kMaxDirectSmallArea) {
             // split into 128x128 work items for the warp-cooperative kernel
@@ -79,7 +79,7 @@ k_raster_big(const TriRecord* __restrict__ tris, const BigItem* __restrict__ ite
         t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
         t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
         BBox r;
-        raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r);
+        raster_region(t.pos0, t.pos1, t.pos2, fp, r);
         int32_t binX = (int32_t)(item.bin & 0xFFFFu) << kBigBinShift, binY = (int32_t)(item.bin >> 16) << kBigBinShift;
         r.minX = max(r.minX, binX); r.minY = max(r.minY, binY);
         r.maxX = min(r.maxX, binX + (1 << kBigBinShift)); r.maxY = min(r.maxY, binY + (1 << kBigBinShift));

@@ -199,6 +199,10 @@ struct swrb_fb {
     // overwrites the layer it reads is ordered after the copy (evCopied).
     cudaEvent_t evReady = nullptr, evCopied = nullptr;
     bool copyPending = false;
+    // scissor rows (swrb_fb_set_scissor_rows): draws, the resolve pass and the GetPixels family only deal with rows [bandY0, bandY1)
+    uint32_t bandY0 = 0, bandY1 = 0;      // bandY1 == 0: the whole framebuffer
+    uint32_t row0() const { return bandY1 ? bandY0 : 0u; }
+    uint32_t row1() const { return bandY1 ? bandY1 : height; }
 };
 
 // An aborted draw (device work list overflow) never touched the depth / id layers; every kernel after it
@@ -806,16 +810,39 @@ static int get_pixels_device_on(swrb_fb* fb, uint32_t layer, void* dst_device, u
     if (rc) return rc;
     rc = fb_order_side_stream(fb, stream);
     if (rc) return rc;
-    uint32_t numVec = fb->width * fb->height / 4;
+    // rows [y0, y1) of the 4x4-tiled layer are one contiguous run of it, and land in rows [y0, y1) of the destination image
+    const uint32_t y0 = fb->row0(), rows = fb->row1() - y0;
+    uint32_t numVec = fb->width * rows / 4;
     // On the device's own stream the copy is on the critical path: fill the machine. On a caller's side
     // stream it runs beside the render kernels (typically storing to a peer GPU over NVLink): one block per
     // SM, four loads in flight per thread.
     const uint32_t grid = stream == d->stream ? grid_for(d, numVec, 256, 8) : std::max(1u, (uint32_t)d->numSMs);
     k_fb_detile<<<grid, 256, 0, stream>>>(
-        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride);
+        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride + (size_t)y0 * fb->width),
+        (uint32_t*)dst_device + (size_t)y0 * stride, fb->width, rows, stride);
     d->launches++;
     CU(cudaGetLastError());
     return fb_side_stream_done(fb, stream);
+}
+
+int swrb_fb_set_scissor_rows(swrb_fb* fb, uint32_t y0, uint32_t y1) {
+    if (!fb) return fail(SWRB_E_INVALID, "fb is null");
+    if (y0 == 0 && (y1 == 0 || y1 == fb->height)) y1 = 0;                      // the whole framebuffer
+    else if (y0 >= y1 || y1 > fb->height || y0 % 8 || (y1 % 8 && y1 != fb->height))
+        return fail(SWRB_E_INVALID, "scissor rows [%u,%u): need y0 < y1 <= %u, y0 a multiple of 8, y1 a multiple of 8 or the height", y0, y1, fb->height);
+    if (y0 == fb->bandY0 && y1 == fb->bandY1) return SWRB_OK;
+    fb->bandY0 = y0; fb->bandY1 = y1;
+    // rows outside the old scissor hold neither the next frame's seeds nor a vis-buffer: the next draw seeds the key buffer afresh,
+    // and cached vertices of meshlets the old scissor dropped are missing
+    fb->keysSeeded = false;
+    if (fb->dev->clipCacheFb == fb) fb->dev->clipCacheFb = nullptr;
+    return SWRB_OK;
+}
+
+int swrb_fb_get_scissor_rows(swrb_fb* fb, uint32_t* y0, uint32_t* y1) {
+    if (!fb || !y0 || !y1) return fail(SWRB_E_INVALID, "null argument");
+    *y0 = fb->row0(); *y1 = fb->row1();
+    return SWRB_OK;
 }
 
 int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride) {
@@ -853,7 +880,8 @@ int swrb_fb_send_pixels(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t 
     // beside the render kernels: one block per SM; measured insensitive to the grid size between 32 and 148 blocks
     // (stores over NVLink are posted, a few hundred KB in flight keep the link busy)
     k_fb_detile_send<<<std::max(1u, (uint32_t)d->numSMs), 256, 0, stream>>>(
-        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride), (uint32_t*)dst_device, fb->width, fb->height, stride, ps);
+        reinterpret_cast<const uint4*>(fb->data + (size_t)layer * fb->layerStride + (size_t)fb->row0() * fb->width),
+        (uint32_t*)dst_device + (size_t)fb->row0() * stride, fb->width, fb->row1() - fb->row0(), stride, ps);
     d->launches++;
     CU(cudaGetLastError());
     return fb_side_stream_done(fb, stream);
@@ -902,8 +930,10 @@ int swrb_fb_get_pixels_async(swrb_fb* fb, uint32_t layer, uint32_t* dst_host, ui
     if (rc) return rc;
     CU(cudaEventRecord(d->detiled[slot], d->stream));
     CU(cudaStreamWaitEvent(d->copyStream, d->detiled[slot], 0));
-    if (stride == fb->width) CU(cudaMemcpyAsync(dst_host, d->detileScratch[slot], need * 4, cudaMemcpyDeviceToHost, d->copyStream));
-    else CU(cudaMemcpy2DAsync(dst_host, (size_t)stride * 4, d->detileScratch[slot], (size_t)fb->width * 4, (size_t)fb->width * 4, fb->height, cudaMemcpyDeviceToHost, d->copyStream));
+    const uint32_t y0 = fb->row0(), rows = fb->row1() - y0;          // scissor rows only, to their place in the host image
+    const uint32_t* src = d->detileScratch[slot] + (size_t)y0 * fb->width;
+    if (stride == fb->width) CU(cudaMemcpyAsync(dst_host + (size_t)y0 * stride, src, (size_t)rows * fb->width * 4, cudaMemcpyDeviceToHost, d->copyStream));
+    else CU(cudaMemcpy2DAsync(dst_host + (size_t)y0 * stride, (size_t)stride * 4, src, (size_t)fb->width * 4, (size_t)fb->width * 4, rows, cudaMemcpyDeviceToHost, d->copyStream));
     CU(cudaEventRecord(d->copied[slot], d->copyStream));
     d->copyInFlight[slot] = true;
     d->hostCopiesPending = true;
@@ -1185,6 +1215,11 @@ static FrameParams frame_params(const swrb_device* d, const swrb_fb* fb, bool bi
     fp.tilesY = (fb->height + kTileSize - 1) >> kTileShift;
     fp.layerStride = fb->layerStride;
     fp.clipMode = binned ? 0u : ((d->flags & SWRB_FLAG_CLIPPING) ? 2u : 1u);          // :567-569 vs :209
+    fp.bandY0 = (int32_t)fb->row0(); fp.bandY1 = (int32_t)fb->row1();
+    fp.bandCull = (fb->row0() != 0 || fb->row1() != fb->height) ? 1u : 0u;
+    // pixel row y holds y/w in [(y - halfH) / halfH, (y + 1 - halfH) / halfH): the band, one row wider on both sides
+    fp.bandNdcLo = (float)(fp.bandY0 - 1 - fp.halfH) / (float)fp.halfH;
+    fp.bandNdcHi = (float)(fp.bandY1 + 1 - fp.halfH) / (float)fp.halfH;
     return fp;
 }
 
@@ -1260,8 +1295,10 @@ static size_t cull_words_needed(const swrb_draw_desc* draws, uint32_t numDraws) 
 
 static void launch_mesh(swrb_device* d, bool binned, uint32_t meshGrid, const swr_meshlet* meshlets, const swr_material* materials, const DrawItem* draws, uint32_t numDraws,
                         uint32_t totalWork, const FrameParams& fp, unsigned long long* keys, const MeshOut& mo, DevCtl* ctl) {
-    if (binned) k_mesh_setup<true><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshlets, materials, draws, numDraws, totalWork, fp, keys, mo, ctl);
-    else k_mesh_setup<false><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshlets, materials, draws, numDraws, totalWork, fp, keys, mo, ctl);
+#define SWRB_MESH(B, S) k_mesh_setup<B, S><<<meshGrid, kMeshWarps * 32, 0, d->stream>>>(meshlets, materials, draws, numDraws, totalWork, fp, keys, mo, ctl)
+    if (fp.bandCull) { if (binned) SWRB_MESH(true, true); else SWRB_MESH(false, true); }
+    else { if (binned) SWRB_MESH(true, false); else SWRB_MESH(false, false); }
+#undef SWRB_MESH
 }
 
 static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_material* materialsDev, const ResolveTexture* texturesDev,
@@ -1722,9 +1759,10 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
                         d->clipCacheMeshlets == scene->meshlets && memcmp(d->clipCacheM, u->ObjectToClip, sizeof(d->clipCacheM)) == 0;
     rp.clipCache = cached ? d->clipCache : nullptr;
     rp.debugLayer = debugLayer;
+    rp.blockY0 = fb->row0() / 8;                     // scissor rows: only those blocks run (multiples of 8 by construction)
     if (debugLayer != SWRB_LAYER_NONE) {            // ResolveDebug: surface only, no lighting, no light markers
         StageScope ss(d, SWRB_STAGE_RESOLVE);
-        dim3 grid((fb->width + 15) / 16, (fb->height + 7) / 8), block(32, kResolveWarps);
+        dim3 grid((fb->width + 15) / 16, (fb->row1() - fb->row0() + 7) / 8), block(32, kResolveWarps);
         if (fromKeys) k_resolve<true, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
         else k_resolve<false, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl);
         d->launches++;
@@ -1746,7 +1784,7 @@ static int resolve_internal(swrb_fb* fb, swrb_scene* scene, const swrb_shading_u
         StageScope ss(d, SWRB_STAGE_RESOLVE);
         // 4 warps = 16 x 8 pixels per block: small blocks pack better beside other contexts' mesh blocks (measured +2 %
         // frames/s over 8-warp blocks, same single-frame time)
-        dim3 grid((fb->width + 15) / 16, (fb->height + 7) / 8), block(32, kResolveWarps);
+        dim3 grid((fb->width + 15) / 16, (fb->row1() - fb->row0() + 7) / 8), block(32, kResolveWarps);
         const bool sky = scene->skyData != nullptr;
         if (sky) rp.sky = scene->sky;
         if (cached) { if (sky) k_resolve<true, true, false, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); else k_resolve<true, true><<<grid, block, 0, d->stream>>>(rp, d->ctl); }

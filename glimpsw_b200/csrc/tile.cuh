@@ -71,7 +71,7 @@ __device__ __forceinline__ void tile_raster_warp(const TriRecord& t, const Frame
                                                  unsigned long long* keys) {
     const uint32_t lane = lane_id();
     BBox r;
-    raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r);
+    raster_region<false>(t.pos0, t.pos1, t.pos2, fp, r);
     r.minX = max(r.minX, tileX0); r.minY = max(r.minY, tileY0);
     r.maxX = min(r.maxX, tileX0 + kTileSize); r.maxY = min(r.maxY, tileY0 + kTileSize);
     Edges e;
@@ -162,7 +162,7 @@ k_tile_raster(const TriRecord* __restrict__ tris, const uint32_t* __restrict__ t
             uint32_t triIdx = j < (listEnd - listBegin) ? binEntries[listBegin + j] : superEntries[bigBegin + (j - (listEnd - listBegin))];
             TriRecord t = load_record(tris, triIdx);
             BBox r;
-            if (raster_region(t.pos0, t.pos1, t.pos2, fp.halfW, fp.halfH, r)) {
+            if (raster_region<false>(t.pos0, t.pos1, t.pos2, fp, r)) {
                 r.minX = max(r.minX, tileX0); r.minY = max(r.minY, tileY0);
                 r.maxX = min(r.maxX, tileX0 + kTileSize); r.maxY = min(r.maxY, tileY0 + kTileSize);
                 int32_t w = r.maxX - r.minX, h = r.maxY - r.minY;

@@ -108,7 +108,9 @@ class PeerComposites:
     launches its local de-tile plus ONE collect kernel (wait for all ready flags -> raise all acks); no host
     synchronisation and no kernel on the render stream. Counts only grow, so nothing is reset across the link."""
 
-    def __init__(self, height: int, width: int, rank: int, world: int, slots: int = 2):
+    def __init__(self, height: int, width: int, rank: int, world: int, slots: int = 2, shared_image: bool = False):
+        """shared_image: every rank stores into the SAME image of a slot — the sort-first split, where each rank's framebuffer has
+        scissor rows and its send moves only its own band (swrb_fb_set_scissor_rows); the flags work as for whole views."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -116,7 +118,8 @@ class PeerComposites:
         self.rank, self.world, self.slots = rank, world, slots
         self.proto = SlotProtocol(world, slots)
         group = dist.group.WORLD.group_name
-        self.buf = symm_mem.empty((slots, world, height, width), dtype=torch.int32, device="cuda")
+        self.shared_image = shared_image
+        self.buf = symm_mem.empty((slots, 1 if shared_image else world, height, width), dtype=torch.int32, device="cuda")
         self.hdl = symm_mem.rendezvous(self.buf, group)
         self.root = self.hdl.get_buffer(0, self.buf.shape, self.buf.dtype)   # rank 0's buffer, mapped into this process
         self.num_flags = self.proto.num_flags            # ready[slot, src] | ack[slot] | one scratch word (see SlotProtocol)
@@ -131,7 +134,7 @@ class PeerComposites:
         self.collected = [torch.cuda.Event() for _ in range(slots)]
 
     def dst_ptr(self, slot: int) -> int:
-        return self.root[slot, self.rank].data_ptr()
+        return self.root[slot, 0 if self.shared_image else self.rank].data_ptr()
 
     def ready_ptr(self, slot: int, src: int) -> int:
         """ready[slot, src] in rank 0's memory."""
@@ -249,3 +252,47 @@ def composite_framebuffer(fb, dst=None, stream=None):
     else:
         composite_keys(t, dst)
     fb.keys_touched()
+
+
+# ---- sort-first: one view split into horizontal bands, one per GPU ------------------------------------------
+def band_rows(height: int, rank: int, world: int, align: int = 128):
+    """Rows [y0, y1) of a `height`-row framebuffer that `rank` of `world` renders: `world` contiguous bands whose boundaries sit on
+    multiples of `align` rows (128 = the reference's bin rows, Rasterizer.h BinSize) while that keeps the largest band within 13 % of
+    height / world; the alignment is halved otherwise, down to 8 rows (what swrb_fb_set_scissor_rows accepts). The bands tile the
+    framebuffer exactly."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    while True:
+        edges = [min(int(round(height * r / world / align)) * align, height) for r in range(world)] + [height]
+        sizes = [b - a for a, b in zip(edges, edges[1:])]
+        if min(sizes) > 0 and (max(sizes) * world <= 1.13 * height or align == 8):
+            return edges[rank], edges[rank + 1]
+        if align == 8:
+            raise ValueError(f"{height} rows cannot be split into {world} bands of multiples of 8 rows")
+        align //= 2
+
+
+def gather_bands(image, rank: int, world: int, bands=None, dst=None):
+    """Sort-first composite: every rank has written its own band of `image` (a [H, W] device tensor, row-major — GetPixels
+    under a scissor fills exactly those rows); afterwards rank `dst` (or every rank when dst is None) holds all bands. No depth
+    compare: the bands are disjoint. Bands of equal size go through one in-place all-gather, ragged ones through broadcasts."""
+    import torch.distributed as dist
+    if world == 1:
+        return
+    h = image.shape[0]
+    bands = bands or [band_rows(h, r, world) for r in range(world)]
+    sizes = {b[1] - b[0] for b in bands}
+    if dst is None and len(sizes) == 1 and bands[0][0] == 0 and bands[-1][1] == h:
+        dist.all_gather_into_tensor(image, image[bands[rank][0]:bands[rank][1]])
+        return
+    if dst is None:
+        for r, (y0, y1) in enumerate(bands):
+            dist.broadcast(image[y0:y1], src=r)
+        return
+    if rank == dst:
+        reqs = [dist.irecv(image[y0:y1], src=r) for r, (y0, y1) in enumerate(bands) if r != dst]
+        for q in reqs:
+            q.wait()
+    else:
+        y0, y1 = bands[rank]
+        dist.send(image[y0:y1], dst=dst)

@@ -164,6 +164,17 @@ SWRB_API int swrb_fb_get_pixels_device(swrb_fb* fb, uint32_t layer, void* dst_de
  * dst may be peer memory of another GPU: the de-tile kernel then stores straight over NVLink. */
 SWRB_API int swrb_fb_get_pixels_device_on_stream(swrb_fb* fb, uint32_t layer, void* dst_device, uint32_t stride, void* cuda_stream);
 
+/* Scissor rows (no reference counterpart; the sort-first split of ONE view over several GPUs): from now on only
+ * pixel rows [y0, y1) of the framebuffer have to come out right. Draws drop the meshlets and triangles that cannot touch
+ * them (conservatively: bound sphere against the band's two planes, then the triangle's pixel box), the resolve pass shades
+ * those rows only, and the GetPixels family (host, device, on-stream, swrb_fb_send_pixels) moves those rows only — to rows
+ * [y0, y1) of the destination image, so N GPUs with disjoint bands fill one image without a depth compare. Inside the band
+ * depth, ids and colour are bit-identical to the unscissored frame; rows outside it are unspecified; the perf counters
+ * count the band's work (a triangle that straddles two bands counts in both). y0 must be a multiple of 8 and y1 a multiple
+ * of 8 or the height; (0, height) or (0, 0) removes the scissor. Set it before the frame's swrb_fb_clear. */
+SWRB_API int swrb_fb_set_scissor_rows(swrb_fb* fb, uint32_t y0, uint32_t y1);
+SWRB_API int swrb_fb_get_scissor_rows(swrb_fb* fb, uint32_t* y0_out, uint32_t* y1_out);
+
 /* Multi-GPU composite exchange (no reference counterpart: the reference is one process). GetPixels whose
  * destination is another GPU's memory (NVLink peer mapping) with the flow control folded into the same kernel:
  * it first waits until *WaitFlag >= WaitValue (a flag in THIS GPU's memory that the consumer raises when the

@@ -168,3 +168,56 @@ def test_sort_last_key_composite_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert depth_ok and ids_ok and covered > 5000 and half_differs > 500
+
+
+# ---- sort-first: horizontal bands, one per rank, gathered without a depth compare -----------------------------
+def test_band_rows_tile_the_framebuffer():
+    for height, world in [(1080, 1), (1080, 2), (1080, 3), (1080, 4), (1080, 8), (1440, 8), (2048, 8), (544, 3), (64, 8), (360, 5)]:
+        bands = [sharding.band_rows(height, r, world) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == height
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        assert all(y1 > y0 and y0 % 8 == 0 and (y1 % 8 == 0 or y1 == height) for y0, y1 in bands)
+        assert max(y1 - y0 for y0, y1 in bands) * world <= 1.13 * height or world * 8 * 4 > height      # balanced unless the bands are tiny
+    assert sharding.band_rows(2048, 3, 8) == (768, 1024)                      # 128-row (bin row) boundaries where they balance
+    with pytest.raises(ValueError):
+        sharding.band_rows(32, 0, 8)
+    with pytest.raises(ValueError):
+        sharding.band_rows(1080, 4, 4)
+
+
+def _sort_first_worker(rank, world, port, height, dst, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    width = 24
+    image = torch.full((height, width), -1, dtype=torch.int32)
+    y0, y1 = sharding.band_rows(height, rank, world)
+    image[y0:y1] = torch.arange(y0, y1, dtype=torch.int32)[:, None] * 1000 + rank      # what this rank's GetPixels under its scissor wrote
+    sharding.gather_bands(image, rank, world, dst=dst)
+    want = torch.empty_like(image)
+    for r in range(world):
+        a, b = sharding.band_rows(height, r, world)
+        want[a:b] = torch.arange(a, b, dtype=torch.int32)[:, None] * 1000 + r
+    if dst is None or rank == dst:
+        q.put((rank, bool(torch.equal(image, want))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,dst", [(2, 512, None), (2, 1080, None), (3, 360, 0), (2, 1080, 1)])
+def test_sort_first_band_gather_gloo(world, height, dst):
+    """Equal bands go through one in-place all-gather, ragged ones through broadcasts, a single destination through send/recv."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sort_first_worker, args=(r, world, port, height, dst, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    expect = world if dst is None else 1
+    got = [q.get(timeout=120) for _ in range(expect)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in got), got
