@@ -11,7 +11,9 @@
 // atomicMax on depth|id keys still reproduces the reference's sequential result.
 // Arithmetic: IEEE, op for op like oracle.cpp::draw_triangle_alpha (canonical approx_rcp = 1/w), so the
 // vis-buffer stays bit-exact. Alpha-tested triangles of any size come here (never to the inline raster or the
-// binner); the mesh kernel writes their records (+ 1/w of the three vertices) to a separate list.
+// binner); the mesh kernel writes their records to a separate list together with 1/w of the three vertices, the three
+// TexCoords words and the material's TextureId | AlphaCutoff (TriRecordW), so a warp here goes record -> texture header ->
+// texels instead of record -> meshlet indices -> TexCoords -> material -> texture header -> texels.
 #pragma once
 
 #include "common.cuh"
@@ -24,6 +26,7 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
                const swr_meshlet* __restrict__ meshlets, const swr_material* __restrict__ materials,
                const ResolveTexture* __restrict__ textures, const float4* __restrict__ clipRemap,
                unsigned long long* __restrict__ keys, DevCtl* __restrict__ ctl) {
+    (void)meshlets; (void)materials;
     const uint32_t n = ctl->overflow ? 0u : ctl->alphaCount;
     const uint32_t lane = lane_id(), i = lane & 15u, half = 0xFFFFu << (lane & 16u);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
@@ -34,23 +37,22 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
         t.pos0 = a.x; t.pos1 = a.y; t.pos2 = a.z; t.z0 = __uint_as_float(a.w);
         t.z1 = __uint_as_float(b.x); t.z2 = __uint_as_float(b.y); t.id = b.z; t.aux = b.w;
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(trisW + it));
+        const uint4 tcm = __ldg(reinterpret_cast<const uint4*>(trisW + it) + 1);      // TexCoords[VertexId[0..2]], TextureId | AlphaCutoff << 24 (written with the record)
         const bool clipped = t.aux == 2u;                                             // a piece from k_clip_triangles: DrawTriangle<FS, true>
         float4 ruv0 = make_float4(0.0f, 1.0f, 0.0f, 0.0f), ruv1 = make_float4(0.0f, 1.0f, 0.0f, 0.0f);
         if (clipped) { ruv0 = __ldg(clipRemap + 2 * it); ruv1 = __ldg(clipRemap + 2 * it + 1); }
 
-        const swr_meshlet* mesh = meshlets + rank_meshlet(t.id);
-        const uint32_t prim = rank_prim(t.id);
         float uv[3][2];
+        {                                                                             // UnpackHalf2x16 of the three TexCoords words
+            const uint32_t tc[3] = { tcm.x, tcm.y, tcm.z };
 #pragma unroll
-        for (int k = 0; k < 3; k++) {                                                 // UnpackHalf2x16 of TexCoords[VertexId[k]]
-            uint32_t vid = __ldg(&mesh->Indices[k][prim]) & 63u;
-            uint32_t tc = __ldg(&mesh->TexCoords[vid]);
-            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&tc));
-            uv[k][0] = f.x; uv[k][1] = f.y;
+            for (int k = 0; k < 3; k++) {
+                float2 f = __half22float2(*reinterpret_cast<const __half2*>(&tc[k]));
+                uv[k][0] = f.x; uv[k][1] = f.y;
+            }
         }
-        const swr_material mat = materials[__ldg(&mesh->MaterialId)];
-        const ResolveTexture& tex = textures[mat.TextureId];
-        const uint32_t cutoff = (uint32_t)mat.AlphaCutoff << 24;
+        const ResolveTexture& tex = textures[tcm.w & 0x00FFFFFFu];
+        const uint32_t cutoff = tcm.w & 0xFF000000u;                                  // AlphaCutoff << 24
         const float scaleLerpU = (float)(tex.width << 8), scaleLerpV = (float)(tex.height << 8);
 
         uint32_t bbMin, bbMax;
@@ -62,10 +64,16 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
 
         const int32_t fragsX = (maxX - minX) >> 2, fragsY = (maxY - minY) >> 2;
         const int32_t numFrags = fragsX * fragsY;
+        // fragment f0 = (fx0, fy0) in row-major order over the box, advanced by two per step without a division
+        int32_t fx0 = 0, fy0 = 0;
         for (int32_t f0 = 0; f0 < numFrags; f0 += 2) {
             const int32_t frag = f0 + (int32_t)(lane >> 4);
             const bool valid = frag < numFrags;
-            const int32_t fx = valid ? frag % fragsX : 0, fy = valid ? frag / fragsX : 0;
+            int32_t fx = fx0 + (int32_t)(lane >> 4), fy = fy0;
+            if (fx >= fragsX) { fx -= fragsX; fy++; }             // the upper half warp's fragment may start the next row (fragsX >= 1)
+            if (!valid) { fx = 0; fy = 0; }
+            fx0 += 2;
+            if (fx0 >= fragsX) { fx0 -= fragsX; fy0++; if (fx0 >= fragsX) { fx0 -= fragsX; fy0++; } }   // fragsX == 1: two rows per step
             const uint32_t px = (uint32_t)(minX + fx * 4) + (i & 3u), py = (uint32_t)(minY + fy * 4) + (i >> 2);
             const uint32_t e0 = (uint32_t)e.e0 + (uint32_t)e.a12 * px + (uint32_t)e.b12 * py;
             const uint32_t e1 = (uint32_t)e.e1 + (uint32_t)e.a20 * px + (uint32_t)e.b20 * py;
@@ -75,6 +83,11 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
 
             float u = __int2float_rn((int32_t)e1), v = __int2float_rn((int32_t)e2);
             const float depth = __fmaf_rn(u, e.z10, __fmaf_rn(v, e.z20, e.z0));       // :296
+            // depth test first, like Shading.cpp:311-313 — and when no pixel of the two fragments can win, nobody needs the texture
+            const uint32_t off = fb_pixel_offset(px, py, fp.width);
+            const unsigned long long key = make_key(depth, t.id);
+            const bool wins = covered && depth > 0.0f && key > __ldcg(keys + off);
+            if (__ballot_sync(0xFFFFFFFFu, wins) == 0) continue;
             // perspective correction (:302-310, :319), canonical rcp = 1/w
             const float pw0 = __fmaf_rn(__fadd_rn(u, v), -W0S, W0);
             const float w = __fmaf_rn(u, W1S, __fmaf_rn(v, W2S, pw0));
@@ -102,13 +115,9 @@ k_raster_alpha(const TriRecord* __restrict__ tris, const TriRecordW* __restrict_
             const int32_t mip = ((((int32_t)__float_as_uint(fmaxf(dx, dy)) - (127 << 23)) >> 23) >> 1) - 8;   // CalcMipLevel - LerpFracBits
             const bool useNearest = (__ballot_sync(0xFFFFFFFFu, valid && mip > 0) & half) != 0;               // Texture.h:432
 
-            if (covered && depth > 0.0f) {
-                const uint32_t off = fb_pixel_offset(px, py, fp.width);
-                const unsigned long long key = make_key(depth, t.id);
-                if (key > __ldcg(keys + off)) {                                       // depth test first, like Shading.cpp:311-313
-                    const uint32_t texel = r_sample_level(tex, tu, tv, 0, mip, useNearest);
-                    if (texel >= cutoff) atomicMax(keys + off, key);                  // :326-330
-                }
+            if (wins) {
+                const uint32_t texel = r_sample_level(tex, tu, tv, 0, mip, useNearest);
+                if (texel >= cutoff) atomicMax(keys + off, key);                      // :326-330
             }
         }
     }

@@ -125,7 +125,14 @@ k_clip_triangles(const uint2* __restrict__ clipList, const swr_meshlet* __restri
                 uint4* dst = reinterpret_cast<uint4*>(alphaTris + slot);
                 dst[0] = recA;
                 dst[1] = make_uint4(__float_as_uint(nz[1]), __float_as_uint(nz[2]), id, 2u);   // aux 2: remap follows
-                *reinterpret_cast<float4*>(alphaW + slot) = make_float4(rw[0], rw[1], rw[2], __uint_as_float(ent.x));
+                uint4* dw = reinterpret_cast<uint4*>(alphaW + slot);
+                dw[0] = make_uint4(__float_as_uint(rw[0]), __float_as_uint(rw[1]), __float_as_uint(rw[2]), ent.x);
+                uint32_t matWord = 0x00FFFFFFu;                                 // the ORIGINAL triangle's TexCoords: the remap below maps the piece's barycentrics back to them
+                if (materialId != SWR_NO_MATERIAL && materials != nullptr) {
+                    const swr_material mat = materials[materialId];
+                    matWord = ((uint32_t)mat.TextureId & 0x00FFFFFFu) | ((uint32_t)mat.AlphaCutoff << 24);
+                }
+                dw[1] = make_uint4(m->TexCoords[m->Indices[0][prim] & 63u], m->TexCoords[m->Indices[1][prim] & 63u], m->TexCoords[m->Indices[2][prim] & 63u], matWord);
                 const ClipVert &p0 = verts[ix[0]], &p1 = verts[ix[1]], &p2 = verts[ix[2]];
                 clipRemap[2 * slot + 0] = make_float4(p0.a[4], __fsub_rn(p1.a[4], p0.a[4]), __fsub_rn(p2.a[4], p0.a[4]), p0.a[5]);   // ClippedU, ClippedV (:462-464)
                 clipRemap[2 * slot + 1] = make_float4(__fsub_rn(p1.a[5], p0.a[5]), __fsub_rn(p2.a[5], p0.a[5]), 0.0f, 0.0f);

@@ -125,10 +125,15 @@ k_raster_gbuffer(const TriRecord* __restrict__ tris, const TriRecordW* __restric
 
         const int32_t fragsX = (maxX - minX) >> 2, fragsY = (maxY - minY) >> 2;
         const int32_t numFrags = fragsX * fragsY;
+        int32_t fx0 = 0, fy0 = 0;                                 // fragment f0 in row-major order over the box, advanced without a division (alpha.cuh)
         for (int32_t f0 = 0; f0 < numFrags; f0 += 2) {
             const int32_t frag = f0 + (int32_t)(lane >> 4);
             const bool valid = frag < numFrags;
-            const int32_t fx = valid ? frag % fragsX : 0, fy = valid ? frag / fragsX : 0;
+            int32_t fx = fx0 + (int32_t)(lane >> 4), fy = fy0;
+            if (fx >= fragsX) { fx -= fragsX; fy++; }
+            if (!valid) { fx = 0; fy = 0; }
+            fx0 += 2;
+            if (fx0 >= fragsX) { fx0 -= fragsX; fy0++; if (fx0 >= fragsX) { fx0 -= fragsX; fy0++; } }
             const uint32_t px = (uint32_t)(minX + fx * 4) + (i & 3u), py = (uint32_t)(minY + fy * 4) + (i >> 2);
             const uint32_t e0 = (uint32_t)e.e0 + (uint32_t)e.a12 * px + (uint32_t)e.b12 * py;
             const uint32_t e1 = (uint32_t)e.e1 + (uint32_t)e.a20 * px + (uint32_t)e.b20 * py;

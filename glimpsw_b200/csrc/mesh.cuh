@@ -321,13 +321,20 @@ k_mesh_setup(const swr_meshlet* __restrict__ meshlets, const swr_material* __res
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             const bool fits = base + numBig <= triCapacity && alphaTris != nullptr;
             if (!fits && lane == 0) atomicExch(&ctl->overflow, 1u);
+            uint32_t matWord = 0x00FFFFFFu;                       // TextureId | AlphaCutoff << 24 for k_raster_alpha (FS_EncodeGBuffer reads the material itself)
+            if (materialId != SWR_NO_MATERIAL && materials != nullptr) {
+                const swr_material mat = materials[materialId];
+                matWord = ((uint32_t)mat.TextureId & 0x00FFFFFFu) | ((uint32_t)mat.AlphaCutoff << 24);
+            }
             for (uint32_t j = lane; fits && j < numBig; j += 32) {
                 const uint32_t prim = s.big[j];
                 uint32_t i0 = idx[prim] & 63u, i1 = idx[128 + prim] & 63u, i2 = idx[256 + prim] & 63u;
                 uint4* dst = reinterpret_cast<uint4*>(alphaTris + base + j);
                 dst[0] = make_uint4(s.pos[i0], s.pos[i1], s.pos[i2], __float_as_uint(s.z[i0]));
                 dst[1] = make_uint4(__float_as_uint(s.z[i1]), __float_as_uint(s.z[i2]), rankBase | ((prim >> 4) << 5) | (prim & 15u), 1u);
-                *reinterpret_cast<float4*>(alphaW + base + j) = make_float4(s.rw[i0], s.rw[i1], s.rw[i2], __uint_as_float(curDraw));   // .w: the draw (DeferredShader reads its ObjectToWorld)
+                uint4* dw = reinterpret_cast<uint4*>(alphaW + base + j);
+                dw[0] = make_uint4(__float_as_uint(s.rw[i0]), __float_as_uint(s.rw[i1]), __float_as_uint(s.rw[i2]), curDraw);   // .w: the draw (DeferredShader reads its ObjectToWorld)
+                dw[1] = make_uint4(__ldg(&m->TexCoords[i0]), __ldg(&m->TexCoords[i1]), __ldg(&m->TexCoords[i2]), matWord);
             }
         } else if (numBig) {
             uint32_t base = 0;

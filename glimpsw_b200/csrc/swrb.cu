@@ -273,6 +273,16 @@ static inline uint32_t grid_for(const swrb_device* d, uint64_t items, uint32_t p
     return (uint32_t)std::max<uint64_t>(1, std::min(need, cap));
 }
 
+// Grid of a kernel whose blocks split a list by a fixed stride: exactly the blocks the GPU keeps resident (registers / shared
+// memory decide how many per SM). A larger grid would run in waves — the first wave's blocks finish their 1/grid of the list,
+// then the rest runs at a fraction of the occupancy.
+template <typename K>
+static uint32_t resident_grid(const swrb_device* d, K kernel, int blockThreads, uint32_t maxPerSM = 8) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, blockThreads, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+    return (uint32_t)d->numSMs * std::min<uint32_t>((uint32_t)perSM, maxPerSM);
+}
+
 static int ensure_buffer(void** ptr, uint64_t* cap, uint64_t need, size_t elem) {
     if (need <= *cap && *ptr != nullptr) return SWRB_OK;
     if (*ptr) CU(cudaFree(*ptr));
@@ -1341,7 +1351,6 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
         d->clipCacheFb = nullptr;
         d->workClean = false;
         fb->keysSeeded = false;                 // the key buffer doubles as this program's scratch
-        const uint32_t recGrid = d->numSMs * 8;
         if (program == SWRB_PROGRAM_OVERDRAW) {
             {
                 StageScope ss(d, SWRB_STAGE_CLEAR);
@@ -1360,7 +1369,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
             }
             {
                 StageScope ss(d, SWRB_STAGE_RASTER);
-                k_raster_overdraw<<<recGrid, 256, 0, d->stream>>>(d->tris, fp, fb->keys, depthLayer, d->ctl);
+                k_raster_overdraw<<<resident_grid(d, k_raster_overdraw, 256), 256, 0, d->stream>>>(d->tris, fp, fb->keys, depthLayer, d->ctl);
                 k_overdraw_finish<<<grid_for(d, (uint64_t)fb->width * fb->height, 256, 8), 256, 0, d->stream>>>(fb->keys, fb->data, fb->width * fb->height, d->ctl);
                 d->launches += 2;
             }
@@ -1448,13 +1457,13 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
             k_raster_direct<<<scatterGrid, 256, 0, d->stream>>>(d->tris, fp, fb->keys, d->bigItems, (uint32_t)std::min<uint64_t>(d->bigItemCap, 0xFFFFFFFFu), d->ctl);
-            k_raster_big<<<d->numSMs * 8, 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
+            k_raster_big<<<resident_grid(d, k_raster_big, 256), 256, 0, d->stream>>>(d->tris, d->bigItems, fp, fb->keys, d->ctl);
             d->launches += 2;
         }
     }
     if (alphaTest && texturesDev != nullptr) {     // FS_EncodeSurfaceId<true> for the alpha list (both raster modes)
         StageScope ss(d, SWRB_STAGE_RASTER);
-        k_raster_alpha<<<d->numSMs * 4, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, fb->keys, d->ctl);
+        k_raster_alpha<<<resident_grid(d, k_raster_alpha, 256), 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, fb->keys, d->ctl);
         d->launches++;
     }
     // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the
@@ -1481,7 +1490,6 @@ static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_
     uint32_t* layer0 = fb->data;
     uint32_t* layer1 = fb->data + fb->layerStride;
     uint32_t* layer2 = fb->data + 2 * (size_t)fb->layerStride;
-    const uint32_t recGrid = d->numSMs * 8;
     const uint32_t numRuns = dl.runStarts ? dl.numRuns : 1u;
     for (uint32_t r = 0; r < numRuns; r++) {
         fp.workBegin = dl.runStarts ? dl.runStarts[r] : 0u;
@@ -1503,9 +1511,9 @@ static int draw_deferred(swrb_fb* fb, const swr_meshlet* meshletsDev, const swr_
         }
         {
             StageScope ss(d, SWRB_STAGE_RASTER);
-            k_raster_gbuffer<false><<<recGrid, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
+            k_raster_gbuffer<false><<<resident_grid(d, k_raster_gbuffer<false>, 256), 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
                                                                      fb->keys, layer0, layer1, layer2, d->ctl);
-            k_raster_gbuffer<true><<<recGrid, 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
+            k_raster_gbuffer<true><<<resident_grid(d, k_raster_gbuffer<true>, 256), 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, dl.items,
                                                                     fb->keys, layer0, layer1, layer2, d->ctl);
             d->launches += 2;
         }
