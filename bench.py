@@ -300,6 +300,38 @@ def run_ours(args):
         r.set_mesh_occupancy(args.mesh_blocks if F > 1 else 4)
         ctxs.append(SimpleNamespace(rast=r, stream=st, fb=r.create_framebuffer(scene.width, scene.height),
                                     scene=r.upload_scene(scene.meshlets, scene.materials, scene.textures, scene.lights), frames={}))
+    # ---- N > 1: deal the views by measured cost instead of v mod N. The views of the batch cost 191..283 us each; with 8 views per
+    # GPU the round-robin deal leaves the slowest rank 7 % over the mean (tools/view_costs.py). Every rank times its round-robin
+    # share once (frames back to back on one context), the 64 costs are all-gathered, and every rank computes the same
+    # longest-first deal with equal counts.
+    deal = {"policy": "v mod N"}
+    if world > 1 and not args.round_robin:
+        c0 = ctxs[0]
+        costs = torch.zeros(num_views, dtype=torch.float64, device="cuda")
+        for v in mine:
+            batch = c0.rast.create_batch(c0.scene, workloads.view_draws(c0.rast, wl, v))
+            frame = c0.rast.make_frame(batch, api.Rasterizer.make_uniforms(**workloads.view_uniforms(wl, v)))
+            for _ in range(2):
+                c0.rast.submit_frame(c0.fb, frame)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(c0.stream)
+            for _ in range(4):
+                c0.rast.submit_frame(c0.fb, frame)
+            e1.record(c0.stream)
+            e1.synchronize()
+            costs[v] = e0.elapsed_time(e1) / 4
+            batch.destroy()
+        dist.all_reduce(costs)                                    # every view was timed by exactly one rank
+        dist.broadcast(costs, src=0)                              # bit-identical on every rank by construction; cheap insurance
+        cost_list = [float(x) for x in costs.cpu()]
+        shares = sharding.deal_views_by_cost(cost_list, world)
+        mean = sum(cost_list) / world
+        deal = {"policy": "longest measured cost first, equal counts (sharding.deal_views_by_cost)",
+                "view_cost_us_min_max": [round(min(cost_list) * 1e3, 1), round(max(cost_list) * 1e3, 1)],
+                "balance_v_mod_N": round(mean / max(sum(cost_list[v] for v in sharding.views_for_rank(num_views, r, world)) for r in range(world)), 4),
+                "balance_this_deal": round(mean / max(sum(cost_list[v] for v in sh) for sh in shares), 4)}
+        mine = shares[rank]
+
     for i, v in enumerate(mine):
         c = ctxs[i % F]
         batch = c.rast.create_batch(c.scene, workloads.view_draws(c.rast, wl, v))
@@ -632,7 +664,8 @@ def run_ours(args):
                        "triangles_per_view": tris, "triangles_per_step": tris * num_views, "meshlets": len(scene.meshlets),
                        "draws_per_view": len(scene.nodes), "mode": args.mode, "frames_in_flight": F,
                        "mesh_kernel_blocks_per_sm": args.mesh_blocks if F > 1 else 4,
-                       "parallelism": f"view-parallel: views dealt v mod {world}" + {
+                       "parallelism": ("view-parallel: views dealt v mod " + str(world) if deal["policy"] == "v mod N" else
+                                       f"view-parallel: the {num_views} views dealt to the {world} GPUs by measured cost, longest first, {len(mine)} each") + {
                            "p2p": ", composites stored by each rank's de-tile kernel straight into rank 0's memory over NVLink (peer memory + device-side flags, 4 slots in flight, tail included)",
                            "nccl": ", composites gathered to rank 0 with NCCL on a side stream (tail included)", "none": ", no gather (diagnostic)",
                            "local": ", composites de-tiled into a device ring buffer on a side stream"}[gather_kind],
@@ -675,6 +708,8 @@ def run_ours(args):
             line["gather_check"] = gather_check
         if nvlink is not None:
             line["nvlink"] = nvlink
+        if world > 1:
+            line["deal"] = deal
         if configs is not None:
             line["configs"] = configs
         if cpu:
@@ -805,6 +840,7 @@ def main():
     ap.add_argument("--ref-views", type=int, default=4, help="--impl reference: views of the batch rendered per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-diag", action="store_true", help="after the e2e leg, time it again with one leg left out at a time (stderr)")
+    ap.add_argument("--round-robin", action="store_true", help="N>1: deal the views v mod N instead of by measured cost")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1/C2/C3/C5) at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
