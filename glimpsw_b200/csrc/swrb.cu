@@ -1463,7 +1463,7 @@ static int draw_list(swrb_fb* fb, const swr_meshlet* meshletsDev, uint32_t numMe
     }
     if (alphaTest && texturesDev != nullptr) {     // FS_EncodeSurfaceId<true> for the alpha list (both raster modes)
         StageScope ss(d, SWRB_STAGE_RASTER);
-        k_raster_alpha<<<resident_grid(d, k_raster_alpha, 256), 256, 0, d->stream>>>(d->alphaTris, d->trisW, fp, meshletsDev, materialsDev, texturesDev, d->clipRemap, fb->keys, d->ctl);
+        k_raster_alpha<<<resident_grid(d, k_raster_alpha, kAlphaWarps * 32), kAlphaWarps * 32, 0, d->stream>>>(d->alphaTris, d->trisW, fp, texturesDev, d->clipRemap, fb->keys, d->ctl);
         d->launches++;
     }
     // The vis-buffer now lives in the key buffer; layers 0/1 are produced on demand (fb_materialize) or the
