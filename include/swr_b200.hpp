@@ -44,6 +44,8 @@ public:
     void Clear(uint32_t color, float depth) { check(swrb_fb_clear(_h, color, depth)); }                       // Rasterizer.h:35-38
     void ClearLayer(uint32_t layer, uint32_t value) { check(swrb_fb_clear_layer(_h, layer, value)); }         // :40-48
     void GetPixels(uint32_t layer, uint32_t* dest, uint32_t stride) { check(swrb_fb_get_pixels(_h, layer, dest, stride)); }   // ImageHelpers.cpp:109
+    // no reference counterpart: sort-first split of one view over several GPUs — only rows [y0, y1) are drawn, resolved and read back
+    void SetScissorRows(uint32_t y0, uint32_t y1) { check(swrb_fb_set_scissor_rows(_h, y0, y1)); }
     // GetLayerData(layer) copies: the raw 4x4-tiled words of one layer
     void DownloadLayer(uint32_t layer, uint32_t* destTiled) { check(swrb_fb_download_tiled(_h, layer, destTiled)); }
     void UploadLayer(uint32_t layer, const uint32_t* srcTiled) { check(swrb_fb_upload_tiled(_h, layer, srcTiled)); }
