@@ -442,6 +442,8 @@ def run_ours(args):
         ev = torch.cuda.Event()
         ev.record(c.stream)
         ctxs[0].stream.wait_event(ev)
+    t_rendered = torch.cuda.Event(enable_timing=True)             # this rank's own views are rendered (the exchange may still be draining)
+    t_rendered.record(ctxs[0].stream)
     if gather_kind != "none":                                     # the last composites are part of the job
         for ev_done in slot_done:
             ctxs[0].stream.wait_event(ev_done)
@@ -452,7 +454,13 @@ def run_ours(args):
     clocks = sampler.stop()
     nvl1 = nvlink_kib(local_rank) if nvl0 else None
     total_ms = t0.elapsed_time(t1)
+    per_rank = None
     if world > 1:
+        mine_ms = torch.tensor([t0.elapsed_time(t_rendered), total_ms], dtype=torch.float64, device="cuda")
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(all_ms, mine_ms)
+        per_rank = {"rendered_ms_per_step": [round(float(x[0]) / args.steps, 4) for x in all_ms],
+                    "done_ms_per_step": [round(float(x[1]) / args.steps, 4) for x in all_ms]}
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
@@ -710,6 +718,7 @@ def run_ours(args):
             line["nvlink"] = nvlink
         if world > 1:
             line["deal"] = deal
+            line["per_rank"] = per_rank
         if configs is not None:
             line["configs"] = configs
         if cpu:
