@@ -22,4 +22,5 @@ run initcheck "smoke()" python -c "import __graft_entry__ as g; g.smoke()"
 run memcheck  "peer send with flow control, deferred + overdraw programs, clipper" python -m pytest -q -x -m gpu tests/test_visbuffer_gpu.py::test_send_pixels_with_flow_control_on_one_gpu "tests/test_deferred_gpu.py::test_gbuffer_bit_exact_on_scenes[direct_clip]" "tests/test_debug_programs.py::test_overdraw_program_bit_exact[binned]"
 run racecheck "peer send with flow control, deferred + overdraw programs, clipper" python -m pytest -q -x -m gpu tests/test_visbuffer_gpu.py::test_send_pixels_with_flow_control_on_one_gpu "tests/test_deferred_gpu.py::test_gbuffer_bit_exact_on_scenes[direct_clip]" "tests/test_debug_programs.py::test_overdraw_program_bit_exact[binned]"
 run memcheck  "scissor rows (band cull, band resolve, band GetPixels) + alpha raster" python -m pytest -q -x -m gpu tests/test_scissor_gpu.py -k "alpha and direct_clip or knot and binned or bands_fill or band_cull"
+run racecheck "alpha raster (shared-memory setup / survivor list per warp)" python -m pytest -q -x -m gpu tests/test_alpha_gpu.py -k binned
 cat $out
