@@ -7,8 +7,10 @@ handedness bits), nodes walked depth-first with `GlobalTransform = parent * loca
 
 What differs from the reference, by necessity (none of its third-party importers exist in this image):
   * cgltf -> the JSON + buffer parsing below (`.gltf` with external / data-URI buffers, and `.glb`);
-  * meshoptimizer's `meshopt_buildMeshlets` -> `adjacency_order` (grow each meshlet over shared vertices, cheapest
-    triangle first) + the cutting scan of `scenes.meshletize` (different meshlet boundaries = different surface ids, same
+  * meshoptimizer's `meshopt_buildMeshlets` -> `build_meshlets_order` (the library's published selection rule: fewest new
+    vertices, dangling triangles first, then the distance / normal-cone score with cone_weight 0.25, k-d tree restarts) (the
+    default) or the simpler `adjacency_order` (cheapest triangle first, no spatial score), each followed by the
+    cutting scan of `scenes.meshletize` (different meshlet boundaries than an upstream import = different surface ids, same
     geometry); `meshopt_computeMeshletBounds` (bounding sphere + normal cone) is restated in `compute_meshlet_bounds`;
   * stb_image -> Pillow for the texture files.
 Everything downstream (the meshlet bytes, materials, texture layout, uniforms) is the reference's format, so an imported
@@ -245,6 +247,112 @@ def adjacency_order(tris: np.ndarray, max_verts: int = 64, max_tris: int = 128) 
     return np.asarray(order, dtype=np.int64)
 
 
+def build_meshlets_order(positions: np.ndarray, tris: np.ndarray, max_verts: int = 64, max_tris: int = 128,
+                         cone_weight: float = 0.25) -> np.ndarray:
+    """Triangle order of meshoptimizer's `meshopt_buildMeshlets(…, 64, 128, cone_weight = 0.25)` (Scene.cpp:215-224), restated from
+    the library's published algorithm (clusterizer.cpp, v1.1 as pinned by the reference's CMakeLists.txt:21; the library itself is not
+    in this image, so ties and floating-point details may differ from an upstream import):
+      * every candidate — a live triangle that shares a vertex with the meshlet under construction — is ranked by `extra`: 0 if it
+        adds no vertex; 1 if it adds some but one of its vertices has no other live triangle left (a dangling triangle is taken now
+        or strands a vertex); else 1 + the number of vertices it adds;
+      * within the best rank the lowest score wins: (1 + distance / expected_radius * (1 - cone_weight)) * max(1e-3, 1 - spread *
+        cone_weight), distance from the meshlet's mean triangle centroid, spread = triangle normal . meshlet's mean normal,
+        expected_radius = sqrt(mean triangle area / 2 * max_tris) / 2;
+      * if that triangle does not fit (vertex or triangle limit) the choice is redone with the topological score (live triangles
+        around its three vertices) — it seeds the next meshlet;
+      * with no candidate left the nearest live triangle to the meshlet's centre (k-d tree over centroids) continues.
+    `scenes.meshletize` cuts the returned stream exactly where the library's appendMeshlet would. Returns a permutation."""
+    tris = np.asarray(tris, dtype=np.int64)
+    n = len(tris)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    from scipy.spatial import cKDTree
+    pos = np.asarray(positions, dtype=np.float64)
+    p0, p1, p2 = pos[tris[:, 0]], pos[tris[:, 1]], pos[tris[:, 2]]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    area = np.linalg.norm(nrm, axis=1)
+    normal = np.where(area[:, None] > 0, nrm / np.maximum(area, 1e-300)[:, None], 0.0)
+    centroid = (p0 + p1 + p2) / 3.0
+    expected_radius = math.sqrt(float(area.sum()) / n * 0.5 * max_tris) * 0.5
+    tree = cKDTree(centroid)
+    T = tris.tolist()
+    adj: list = [[] for _ in range(int(tris.max()) + 1)]
+    for t, (a, b, c) in enumerate(T):
+        for v in dict.fromkeys((a, b, c)):
+            adj[v].append(t)
+    live = np.array([len(x) for x in adj], dtype=np.int64)         # live triangles around every vertex
+    emitted = np.zeros(n, dtype=bool)
+    order: list = []
+    used: set = set()                                              # vertices of the meshlet under construction
+    missing: dict = {}                                             # candidate triangle -> vertices it would add
+    num_tris = 0
+    acc_c, acc_n = np.zeros(3), np.zeros(3)
+
+    def reset():
+        nonlocal num_tris, acc_c, acc_n
+        used.clear()
+        missing.clear()
+        num_tris = 0
+        acc_c, acc_n = np.zeros(3), np.zeros(3)
+
+    def select(use_cone: bool):
+        cand = np.fromiter(missing.keys(), dtype=np.int64, count=len(missing))
+        miss = np.fromiter(missing.values(), dtype=np.int64, count=len(missing))
+        dangling = (live[tris[cand]] == 1).any(axis=1)
+        extra = np.where(miss == 0, 0, np.where(dangling, 1, miss + 1))
+        best = extra.min()
+        pick = np.nonzero(extra == best)[0]
+        sel = cand[pick]
+        if use_cone and num_tris:
+            center = acc_c / num_tris
+            ln = np.linalg.norm(acc_n)
+            axis = acc_n / ln if ln > 0 else acc_n
+            dist = np.linalg.norm(centroid[sel] - center, axis=1)
+            spread = normal[sel] @ axis
+            score = (1.0 + dist / expected_radius * (1.0 - cone_weight)) * np.maximum(1e-3, 1.0 - spread * cone_weight)
+        else:
+            score = live[tris[sel]].sum(axis=1) - 3
+        k = int(np.argmin(score))
+        return int(sel[k]), int(miss[pick[k]])
+
+    while len(order) < n:
+        t = None
+        if missing:
+            t, add = select(True)
+            if len(used) + add > max_verts or num_tris >= max_tris:
+                t, add = select(False)
+        if t is None:                                              # nothing adjacent: continue with the nearest live triangle
+            center = acc_c / num_tris if num_tris else np.zeros(3)
+            k = 8
+            while t is None:
+                _, idx = tree.query(center, k=min(k, n))
+                for j in np.atleast_1d(idx).tolist():
+                    if not emitted[j]:
+                        t = j
+                        break
+                k *= 8
+            add = len({v for v in T[t] if v not in used})
+        if len(used) + add > max_verts or num_tris >= max_tris:    # appendMeshlet: the meshlet is full, t opens the next one
+            reset()
+        emitted[t] = True
+        order.append(t)
+        missing.pop(t, None)
+        num_tris += 1
+        acc_c = acc_c + centroid[t]
+        acc_n = acc_n + normal[t]
+        for v in dict.fromkeys(T[t]):
+            live[v] -= 1
+            adj[v].remove(t)
+        for v in dict.fromkeys(T[t]):
+            if v in used:
+                continue
+            used.add(v)
+            for u in adj[v]:                                       # its live triangles become candidates / need one vertex less
+                k = missing.get(u)
+                missing[u] = (len({x for x in T[u] if x not in used}) if k is None else k - 1)
+    return np.asarray(order, dtype=np.int64)
+
+
 def _bounding_sphere(points: np.ndarray):
     """meshoptimizer's computeBoundingSphere (clusterizer.cpp, v1.1 as pinned by the reference's CMakeLists.txt:21; restated from
     the published algorithm, float32 throughout): the extreme points along the three axes give three candidate diameters, the
@@ -308,9 +416,14 @@ def compute_meshlet_bounds(meshlets: np.ndarray) -> None:
 
 
 def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Camera | None = None,
-                flip_winding: bool = False) -> SceneData:
+                flip_winding: bool = False, builder: str = "meshopt") -> SceneData:
     """Scene::ImportGltf. Returns a SceneData (meshlets, one DrawNode per glTF node with a mesh, materials, textures,
-    lights). `flip_winding` swaps two indices of every triangle (for assets authored with the other front face)."""
+    lights). `flip_winding` swaps two indices of every triangle (for assets authored with the other front face).
+    `builder`: "meshopt" = `build_meshlets_order`, the library's scored selection (cone_weight 0.25 like Scene.cpp:215; what the
+    committed Sponza fixture is built with); "adjacency" = `adjacency_order`, the quick topological stand-in (on Sponza_LowPoly its
+    meshlets' bounding spheres are six times larger on average)."""
+    if builder not in ("adjacency", "meshopt"):
+        raise ValueError(f"unknown meshlet builder {builder!r}")
     g = GltfFile(path)
     js = g.json
     materials = np.zeros(len(js.get("materials", [])), dtype=MATERIAL_DTYPE)
@@ -340,7 +453,7 @@ def import_gltf(path: str, width: int = 1920, height: int = 1080, camera: cam.Ca
             if nrm is not None and tan is None:
                 tan = np.zeros((len(pos), 4), dtype=f32)                        # glm::vec4 tangent = 0 (Scene.cpp:258)
             mat_id = prim.get("material", None)
-            tris = tris[adjacency_order(tris)]                                   # meshopt_buildMeshlets stand-in (Scene.cpp:218-221)
+            tris = tris[adjacency_order(tris) if builder == "adjacency" else build_meshlets_order(pos, tris)]   # meshopt_buildMeshlets (Scene.cpp:218-224)
             m = meshletize(pos, tris, uv=uv, normals=nrm, tangents=tan,
                            material_id=NO_MATERIAL if mat_id is None else mat_id,
                            alpha_cutoff=255 if mat_id is None else int(materials[mat_id]["AlphaCutoff"]))
